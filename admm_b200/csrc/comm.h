@@ -1,0 +1,30 @@
+// comm.h -- the one collective this library needs: sum all-reduce over NVLink via NCCL.
+//
+// One process per GPU; the host program (bench.py / the R session's launcher) creates the
+// communicator with b200admm_comm_id + b200admm_comm_init.  NCCL is bound at run time with
+// dlopen("libnccl.so.2") so that libb200admm.so has no link-time dependency on it and reuses
+// the copy a host process may already have loaded.  With no communicator installed every
+// call below is a no-op on a "world" of one rank.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct Comm {
+    int rank = 0;
+    int nranks = 1;
+    void* handle = nullptr;       // ncclComm_t
+    bool active() const { return handle != nullptr && nranks > 1; }
+};
+Comm& comm();
+
+void comm_unique_id(void* id128);
+void comm_init(const void* id128, int rank, int nranks);
+void comm_destroy();
+
+void allreduce_sum(cudaStream_t s, float* buf, size_t count);
+void allreduce_sum(cudaStream_t s, double* buf, size_t count);
+// host scalars through a small device staging buffer (setup only)
+double allreduce_sum_host(cudaStream_t s, double v);
+
+}  // namespace b200

@@ -1,0 +1,417 @@
+// fadmm_tall.cu -- the per-iteration hot path of the lasso / elastic-net solver for n > p,
+// as ONE persistent cooperative kernel that runs the whole lambda path on the device.
+//
+// Reference being replaced (all in /root/reference/src):
+//   FADMMBase::solve / update_x / update_z / update_y / converged      FADMMBase.h:185-265
+//   ADMMLassoTall::next_x / next_z / next_residual / soft_threshold     ADMMLassoTall.h:55-95
+//   ADMMLassoTall::compute_eps_* / compute_resid_* / diff_squared_norm  ADMMLassoTall.h:102-161
+//   ADMMLassoTall::init_warm                                            ADMMLassoTall.h:219-230
+//   ADMMEnetTall::enet                                                  ADMMEnet.h:24-45
+//   the lambda loop of admm_lasso()                                     Lasso.cpp:97-124
+//
+// Data flow of one iteration (grid = one CTA per SM, 512 threads, state vectors in L2):
+//   [A] x_own = Kinv[own rows, :] * rhs        rhs (p floats) lives in shared memory; each CTA
+//       streams its contiguous row panel of Kinv = (X'X + rho I)^-1 from HBM exactly once with
+//       128-bit L1-bypassing loads, 8 loads in flight per lane.  This is the only HBM traffic
+//       of the iteration: 4 p^2 bytes.
+//   [B] own rows: z = prox(x + adj_y/rho); r = x - z; y = adj_y + rho r; six partial sums
+//       (|r|^2, |z-z_old|^2, |z-adj_z|^2, |x|^2, |z|^2, |y|^2): warp shuffle -> CTA -> global slot.
+//   ---- one grid barrier (release/acquire counter) ----
+//   [C] every CTA reduces the G x 6 partials in the same fixed order (bitwise identical
+//       scalars everywhere), evaluates the stopping rule, the combined residual and the
+//       restart test, then forms adj_z / adj_y for ALL p entries straight into the next rhs
+//       in shared memory (4 L2-resident vectors), storing only its own rows of adj_*.
+// z and y are triple-buffered and the partial sums double-buffered, which is what makes a
+// single barrier per iteration race-free (a fast CTA can be at most one barrier ahead).
+//
+// Mixed precision follows the reference: vectors float, scalars double; double scalars are
+// rounded to float where Eigen would do so (rho * r, adj_y / rho, (1+t) * z), and the prox
+// compares/subtracts in double (ADMMLassoTall.h:64-67).  No FMA contraction is allowed on
+// those expressions (explicit __fmul_rn/__fadd_rn), so one iteration differs from the CPU
+// restatement only through the summation order of the norms and of the K^-1 product.
+#include "common.cuh"
+#include "kernels.h"
+#include <algorithm>
+
+namespace b200 {
+
+namespace {
+
+constexpr int TP_THREADS = 512;
+constexpr int TP_WARPS = TP_THREADS / 32;
+constexpr int TP_SEG = 4;            // each row is split into 4 segments -> (row, segment) tasks
+constexpr int NSUM = 6;
+constexpr int PART_STRIDE = 8;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// all CTAs of the (co-resident, cooperative) grid
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_add_u64(ctr, 1ULL);
+        while (ld_acquire_u64(ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct ProxParams {
+    int enet;
+    double pen;          // lambda / rho
+    float thresh, denom; // enet only
+};
+__device__ __forceinline__ float prox_apply(float v, const ProxParams& q)
+{
+    if (!q.enet) {
+        if ((double)v > q.pen) return (float)((double)v - q.pen);
+        if ((double)v < -q.pen) return (float)((double)v + q.pen);
+        return 0.f;
+    }
+    if (v > q.thresh) return __fdiv_rn(__fsub_rn(v, q.thresh), q.denom);
+    if (v < -q.thresh) return __fdiv_rn(__fadd_rn(v, q.thresh), q.denom);
+    return 0.f;
+}
+__device__ __forceinline__ ProxParams make_prox(int enet, float lambda, double rho, double alpha_d)
+{
+    ProxParams q;
+    q.enet = enet;
+    q.pen = (double)lambda / rho;
+    const float alpha = (float)alpha_d;
+    q.thresh = (float)((double)alpha * q.pen);
+    q.denom = (float)(1.0 + q.pen * (1.0 - (double)alpha));
+    return q;
+}
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a, int rows_per_cta, int ld)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* rhs = smem;                                   // ld floats (ld = p rounded up to 4)
+    float* xpart = smem + ld;                            // rows_per_cta * TP_SEG
+    __shared__ double s_sum[NSUM];
+    __shared__ float s_red[TP_WARPS][NSUM];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int p = a.p;
+    const int r0 = min(p, cta * rows_per_cta), r1 = min(p, r0 + rows_per_cta);
+    const int nrows = r1 - r0;
+    const int ntasks = nrows * TP_SEG;
+    const int segv = ((ld / 4) + TP_SEG - 1) / TP_SEG;   // float4 per segment
+    const int nvec = ld / 4;
+
+    auto zb = [&](int i) -> float* { return a.state + (size_t)i * ld; };          // triple-buffered z
+    auto yb = [&](int i) -> float* { return a.state + (size_t)(3 + i) * ld; };    // triple-buffered y
+    float* adj_z = a.state + 6 * (size_t)ld;
+    float* adj_y = a.state + 7 * (size_t)ld;
+    float* partials = a.state + 8 * (size_t)ld;          // [2][G][PART_STRIDE]
+
+    const double rho = a.rho;
+    const float frho = (float)rho;
+    const double sqrt_p = sqrt((double)p);
+
+    // scalars replicated (bitwise identically) in every thread of every CTA
+    double sx2 = 0.0, sz2 = 0.0, sy2 = 0.0;              // |x|^2, |z|^2, |y|^2 of the current iterate
+    double adj_a = 1.0, adj_c = 9999.0;
+    int cur = 0;                                          // buffer holding the current z / y
+    unsigned long long nbar = 0;
+    unsigned git = 0;                                     // global iteration counter (buffer parity)
+
+    for (int k = 0; k < a.nl; k++) {
+        const float lambda = (float)a.lambdas[k];
+        const ProxParams prox = make_prox(a.enet, lambda, rho, a.alpha);
+        const bool tracing = (a.trace != nullptr) && (k == a.trace_lambda);
+
+        // rhs = XY - adj_y + rho * adj_z from the stored extrapolation (cold start: zeros)
+        for (int v = tid; v < nvec; v += TP_THREADS) {
+            const float4 xy = __ldg(reinterpret_cast<const float4*>(a.XY) + v);
+            const float4 ay = ldcg4(adj_y + 4 * v), az = ldcg4(adj_z + 4 * v);
+            float4 o;
+            o.x = (float)((double)__fsub_rn(xy.x, ay.x) + rho * (double)az.x);
+            o.y = (float)((double)__fsub_rn(xy.y, ay.y) + rho * (double)az.y);
+            o.z = (float)((double)__fsub_rn(xy.z, ay.z) + rho * (double)az.z);
+            o.w = (float)((double)__fsub_rn(xy.w, ay.w) + rho * (double)az.w);
+            reinterpret_cast<float4*>(rhs)[v] = o;
+        }
+        __syncthreads();
+
+        int niter = a.maxit + 1;
+        for (int it = 0; it < a.maxit; it++, git++) {
+            const int nxt = (cur + 1) % 3;
+            // tolerances from the iterate before this step (FADMMBase.h:187-188)
+            const double eps_primal = fmax((double)sqrtf((float)sx2), (double)sqrtf((float)sz2)) * a.eps_rel + sqrt_p * a.eps_abs;
+            const double eps_dual = (double)sqrtf((float)sy2) * a.eps_rel + sqrt_p * a.eps_abs;
+
+            // ---- [A] x_own = Kinv[own rows] * rhs -------------------------------------------------
+            const bool rev = a.snake && (git & 1u);
+            for (int t0 = warp; t0 < ntasks; t0 += TP_WARPS) {
+                const int t = rev ? (ntasks - 1 - t0) : t0;
+                const int row = t / TP_SEG, seg = t % TP_SEG;
+                const float4* m = reinterpret_cast<const float4*>(a.Kinv + (size_t)(r0 + row) * ld);
+                const float4* rv = reinterpret_cast<const float4*>(rhs);
+                const int v0 = seg * segv, v1 = min(nvec, v0 + segv);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                // 8 predicated 128-bit loads in flight per lane, also in the ragged last sweep
+                for (int v = v0 + lane; v < v1; v += 8 * 32) {
+                    float4 q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int idx = v + u * 32;
+                        q[u] = idx < v1 ? ld_stream_f4(m + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u += 4) {
+                        const int i0 = min(v + u * 32, v1 - 1), i1 = min(v + (u + 1) * 32, v1 - 1);
+                        const int i2 = min(v + (u + 2) * 32, v1 - 1), i3 = min(v + (u + 3) * 32, v1 - 1);
+                        const float4 b0 = rv[i0], b1 = rv[i1], b2 = rv[i2], b3 = rv[i3];
+                        s0 = fmaf(q[u].x, b0.x, s0); s0 = fmaf(q[u].y, b0.y, s0); s0 = fmaf(q[u].z, b0.z, s0); s0 = fmaf(q[u].w, b0.w, s0);
+                        s1 = fmaf(q[u + 1].x, b1.x, s1); s1 = fmaf(q[u + 1].y, b1.y, s1); s1 = fmaf(q[u + 1].z, b1.z, s1); s1 = fmaf(q[u + 1].w, b1.w, s1);
+                        s2 = fmaf(q[u + 2].x, b2.x, s2); s2 = fmaf(q[u + 2].y, b2.y, s2); s2 = fmaf(q[u + 2].z, b2.z, s2); s2 = fmaf(q[u + 2].w, b2.w, s2);
+                        s3 = fmaf(q[u + 3].x, b3.x, s3); s3 = fmaf(q[u + 3].y, b3.y, s3); s3 = fmaf(q[u + 3].z, b3.z, s3); s3 = fmaf(q[u + 3].w, b3.w, s3);
+                    }
+                }
+                const float s = warp_sum((s0 + s1) + (s2 + s3));
+                if (lane == 0) xpart[t] = s;
+            }
+            __syncthreads();
+
+            // ---- [B] own rows: z, residual, y, partial sums -------------------------------------
+            float ps[NSUM] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int r = tid; r < nrows; r += TP_THREADS) {
+                const int i = r0 + r;
+                const float xv = (xpart[r * TP_SEG] + xpart[r * TP_SEG + 1]) + (xpart[r * TP_SEG + 2] + xpart[r * TP_SEG + 3]);
+                const float ay = __ldcg(adj_y + i), az = __ldcg(adj_z + i), zo = __ldcg(zb(cur) + i);
+                const float v = __fadd_rn(xv, __fdiv_rn(ay, frho));
+                const float zn = prox_apply(v, prox);
+                const float res = __fsub_rn(xv, zn);
+                const float yn = __fadd_rn(ay, __fmul_rn(frho, res));
+                zb(nxt)[i] = zn;
+                yb(nxt)[i] = yn;
+                const float d1 = zn - zo, d2 = zn - az;
+                ps[0] += res * res; ps[1] += d1 * d1; ps[2] += d2 * d2;
+                ps[3] += xv * xv;   ps[4] += zn * zn; ps[5] += yn * yn;
+            }
+#pragma unroll
+            for (int q = 0; q < NSUM; q++) ps[q] = warp_sum(ps[q]);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < NSUM; q++) s_red[warp][q] = ps[q];
+            }
+            __syncthreads();
+            if (tid < NSUM) {
+                float s = 0.f;
+                for (int w = 0; w < TP_WARPS; w++) s += s_red[w][tid];
+                partials[((size_t)(git & 1u) * G + cta) * PART_STRIDE + tid] = s;
+            }
+
+            nbar++;
+            grid_barrier(a.barrier, nbar * (unsigned long long)G);
+
+            // ---- [C] global scalars, identical in every CTA ----------------------------------------
+            if (warp < NSUM) {
+                double s = 0.0;
+                const float* src = partials + (size_t)(git & 1u) * G * PART_STRIDE + warp;
+                for (int c = lane; c < G; c += 32) s += (double)__ldcg(src + (size_t)c * PART_STRIDE);
+                s = warp_sum(s);
+                if (lane == 0) s_sum[warp] = s;
+            }
+            __syncthreads();
+            const double sum_r2 = s_sum[0], sum_dz2 = s_sum[1], sum_da2 = s_sum[2];
+            sx2 = s_sum[3]; sz2 = s_sum[4]; sy2 = s_sum[5];
+            const double resid_primal = (double)sqrtf((float)sum_r2);
+            const double resid_dual = rho * sqrt((double)(float)sum_dz2);
+            const int old = cur;
+            cur = nxt;
+
+            if (tracing && cta == 0 && tid == 0 && it < a.trace_cap) {
+                double* row = a.trace + 5 * (size_t)it;
+                row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
+                *a.trace_rows = it + 1;
+            }
+            if (resid_primal < eps_primal && resid_dual < eps_dual) { niter = it + 1; git++; break; }
+
+            const double old_c = adj_c;
+            adj_c = rho * resid_primal * resid_primal + rho * (double)(float)sum_da2;
+            bool accel;
+            float c1 = 0.f, c2 = 0.f;
+            if (adj_c < 0.999 * old_c) {
+                const double old_a = adj_a;
+                adj_a = 0.5 + 0.5 * sqrt(1.0 + 4.0 * old_a * old_a);
+                const double ratio = (old_a - 1.0) / adj_a;
+                c1 = (float)(1.0 + ratio); c2 = (float)ratio;
+                accel = true;
+            } else {
+                adj_a = 1.0;
+                adj_c = old_c / 0.999;
+                accel = false;
+            }
+            // next rhs for all entries; own rows of adj_* stored for phase [B] / later warm starts
+            const float* zn_ = zb(cur); const float* zo_ = zb(old);
+            const float* yn_ = yb(cur); const float* yo_ = yb(old);
+            for (int v = tid; v < nvec; v += TP_THREADS) {
+                const float4 zo = ldcg4(zo_ + 4 * v), yo = ldcg4(yo_ + 4 * v);
+                float4 az, ay;
+                if (accel) {
+                    const float4 zn = ldcg4(zn_ + 4 * v), yn = ldcg4(yn_ + 4 * v);
+                    az.x = __fsub_rn(__fmul_rn(c1, zn.x), __fmul_rn(c2, zo.x));
+                    az.y = __fsub_rn(__fmul_rn(c1, zn.y), __fmul_rn(c2, zo.y));
+                    az.z = __fsub_rn(__fmul_rn(c1, zn.z), __fmul_rn(c2, zo.z));
+                    az.w = __fsub_rn(__fmul_rn(c1, zn.w), __fmul_rn(c2, zo.w));
+                    ay.x = __fsub_rn(__fmul_rn(c1, yn.x), __fmul_rn(c2, yo.x));
+                    ay.y = __fsub_rn(__fmul_rn(c1, yn.y), __fmul_rn(c2, yo.y));
+                    ay.z = __fsub_rn(__fmul_rn(c1, yn.z), __fmul_rn(c2, yo.z));
+                    ay.w = __fsub_rn(__fmul_rn(c1, yn.w), __fmul_rn(c2, yo.w));
+                } else { az = zo; ay = yo; }
+                const float4 xy = __ldg(reinterpret_cast<const float4*>(a.XY) + v);
+                float4 o;
+                o.x = (float)((double)__fsub_rn(xy.x, ay.x) + rho * (double)az.x);
+                o.y = (float)((double)__fsub_rn(xy.y, ay.y) + rho * (double)az.y);
+                o.z = (float)((double)__fsub_rn(xy.z, ay.z) + rho * (double)az.z);
+                o.w = (float)((double)__fsub_rn(xy.w, ay.w) + rho * (double)az.w);
+                reinterpret_cast<float4*>(rhs)[v] = o;
+                const int i = 4 * v;
+                if (i + 3 >= r0 && i < r1) {
+                    const float azv[4] = {az.x, az.y, az.z, az.w}, ayv[4] = {ay.x, ay.y, ay.z, ay.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (i + e >= r0 && i + e < r1) { adj_z[i + e] = azv[e]; adj_y[i + e] = ayv[e]; }
+                }
+            }
+            __syncthreads();
+        }
+        if (niter == a.maxit + 1) { /* loop ran out: git already advanced by the for-increment */ }
+
+        // solution at this lambda = current z (own rows)
+        for (int r = tid; r < nrows; r += TP_THREADS) a.z_out[(size_t)k * p + r0 + r] = __ldcg(zb(cur) + r0 + r);
+        if (cta == 0 && tid == 0) a.niter_out[k] = niter;
+    }
+}
+
+// stand-alone fused pass over long vectors (HBM-bound when len >> L2)
+constexpr int ZU_THREADS = 256;
+__global__ void __launch_bounds__(ZU_THREADS) fused_zu_kernel(const float* __restrict__ x, const float* __restrict__ adj_y,
+                                                              const float* __restrict__ old_z, const float* __restrict__ adj_z,
+                                                              float* __restrict__ z, float* __restrict__ y, i64 len,
+                                                              float lambda, double rho, int enet, double alpha, float* __restrict__ part)
+{
+    const ProxParams prox = make_prox(enet, lambda, rho, alpha);
+    const float frho = (float)rho;
+    float ps[NSUM] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const i64 nvec = len / 4;
+    const i64 stride = (i64)gridDim.x * ZU_THREADS;
+    auto one = [&](float xv, float ay, float zo, float az, float& zn, float& yn) {
+        const float v = __fadd_rn(xv, __fdiv_rn(ay, frho));
+        zn = prox_apply(v, prox);
+        const float res = __fsub_rn(xv, zn);
+        yn = __fadd_rn(ay, __fmul_rn(frho, res));
+        const float d1 = zn - zo, d2 = zn - az;
+        ps[0] += res * res; ps[1] += d1 * d1; ps[2] += d2 * d2;
+        ps[3] += xv * xv;   ps[4] += zn * zn; ps[5] += yn * yn;
+    };
+    for (i64 v = (i64)blockIdx.x * ZU_THREADS + threadIdx.x; v < nvec; v += stride) {
+        const float4 xv = ld_stream_f4(reinterpret_cast<const float4*>(x) + v);
+        const float4 ay = ld_stream_f4(reinterpret_cast<const float4*>(adj_y) + v);
+        const float4 zo = ld_stream_f4(reinterpret_cast<const float4*>(old_z) + v);
+        const float4 az = ld_stream_f4(reinterpret_cast<const float4*>(adj_z) + v);
+        float4 zn, yn;
+        one(xv.x, ay.x, zo.x, az.x, zn.x, yn.x);
+        one(xv.y, ay.y, zo.y, az.y, zn.y, yn.y);
+        one(xv.z, ay.z, zo.z, az.z, zn.z, yn.z);
+        one(xv.w, ay.w, zo.w, az.w, zn.w, yn.w);
+        __stcs(reinterpret_cast<float4*>(z) + v, zn);
+        __stcs(reinterpret_cast<float4*>(y) + v, yn);
+    }
+    if (blockIdx.x == 0) {
+        for (i64 i = nvec * 4 + threadIdx.x; i < len; i += ZU_THREADS) {
+            float zn, yn;
+            one(x[i], adj_y[i], old_z[i], adj_z[i], zn, yn);
+            z[i] = zn; y[i] = yn;
+        }
+    }
+    __shared__ float s_red[ZU_THREADS / 32][NSUM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NSUM; q++) ps[q] = warp_sum(ps[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NSUM; q++) s_red[warp][q] = ps[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < NSUM) {
+        float s = 0.f;
+        for (int w = 0; w < ZU_THREADS / 32; w++) s += s_red[w][threadIdx.x];
+        part[(size_t)blockIdx.x * NSUM + threadIdx.x] = s;
+    }
+}
+__global__ void fused_zu_finish_kernel(const float* __restrict__ part, int nblocks, double* __restrict__ sums)
+{
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q >= NSUM) return;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += (double)part[(size_t)b * NSUM + q];
+    s = warp_sum(s);
+    if (lane == 0) sums[q] = s;
+}
+
+}  // namespace
+
+size_t tall_state_floats(int p)
+{
+    const size_t ld = ((size_t)p + 3) & ~(size_t)3;
+    return 8 * ld + 2 * (size_t)1024 * PART_STRIDE;
+}
+
+int launch_tall_path(cudaStream_t s, const TallPathArgs& a)
+{
+    const int p = a.p;
+    const int ld = (p + 3) & ~3;
+    const int sms = sm_count();
+    // enough rows per CTA to amortise the barrier; never more CTAs than SMs (co-residency)
+    int G = std::min(sms, std::max(1, (p + 7) / 8));
+    int rows_per_cta = (p + G - 1) / G;
+    rows_per_cta = (rows_per_cta + 3) & ~3;
+    G = std::min(G, (p + rows_per_cta - 1) / rows_per_cta);
+    const size_t smem = sizeof(float) * ((size_t)ld + (size_t)rows_per_cta * TP_SEG);
+    if (smem > 200 * 1024) throw ArgError("tall path: p too large for the shared-memory resident rhs (p <= 50000)");
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(tall_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    int occ = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tall_path_kernel, TP_THREADS, smem));
+    if (occ < 1) throw CudaError("tall path kernel does not fit on an SM");
+    TallPathArgs args = a;
+    int rpc = rows_per_cta, ldi = ld;
+    void* params[] = { (void*)&args, (void*)&rpc, (void*)&ldi };
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tall_path_kernel, dim3(G), dim3(TP_THREADS), params, smem, s));
+    ++g_launch_count;
+    return G;
+}
+
+int fused_zu_blocks() { return sm_count() * 8; }
+
+void fused_zu_pass(cudaStream_t s, const float* x, const float* adj_y, const float* old_z, const float* adj_z,
+                   float* z, float* y, i64 len, double lambda, double rho, int enet, double alpha,
+                   double* sums_dev, float* partial_work)
+{
+    const int nb = fused_zu_blocks();
+    fused_zu_kernel<<<nb, ZU_THREADS, 0, s>>>(x, adj_y, old_z, adj_z, z, y, len, (float)lambda, rho, enet, alpha, partial_work);
+    KERNEL_CHECK();
+    fused_zu_finish_kernel<<<1, 32 * NSUM, 0, s>>>(partial_work, nb, sums_dev);
+    KERNEL_CHECK();
+}
+
+}  // namespace b200

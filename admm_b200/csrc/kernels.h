@@ -1,0 +1,94 @@
+// kernels.h -- host-callable launchers of the CUDA kernels in this directory.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- gemm.cu -----------------------------------------------------------------------------
+enum GemmMode {
+    GEMM_LOWER        = 1,    // compute / store only C(i,j) with i >= j (square C)
+    GEMM_MIRROR       = 2,    // additionally store C(j,i) = C(i,j)  (with GEMM_LOWER)
+    GEMM_A_LOWER_TRI  = 4,    // op(A)=A,  A lower triangular: skip + mask k > i
+    GEMM_AT_LOWER_TRI = 8,    // op(A)=A', A lower triangular: skip + mask k < i
+    GEMM_B_LOWER_TRI  = 16,   // op(B)=B,  B lower triangular: skip + mask k < j
+    GEMM_BT_LOWER_TRI = 32,   // op(B)=B', B lower triangular: skip + mask k > j
+};
+template <class T>
+void gemm(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const T* A, i64 lda,
+          const T* B, i64 ldb, T beta, T* C, i64 ldc, int mode);
+
+// ---- gram_tc.cu : X'X on the tcgen05 tensor cores (3xTF32 split, fp32-accurate) ------------
+// returns false if the shape cannot use the tensor path (caller falls back to gemm<float>)
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 p, float* G /* p x p full */);
+
+// ---- gemv.cu -----------------------------------------------------------------------------
+// out[j] = sum_i A(i,j) v[i]   (A m x ncol column-major, lda)  -- one dot product per column
+template <class T> void gemv_t(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T* out);
+// out[i] = sum_j A(i,j) v[j]   -- row-parallel; `work` must hold gemv_n_work(m, ncol) entries
+template <class T> void gemv_n(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T* out, T* work);
+size_t gemv_n_work(i64 m, i64 ncol);
+
+// ---- stdize.cu ---------------------------------------------------------------------------
+// DataStd (/root/reference/src/DataStd.h:89-155).  flag = standardize + 2*intercept.
+// X_out may alias X_in.  meanX / scaleX: device arrays of length p (written as the flag requires).
+// tmp: 2 * p scratch entries (device).
+template <class T>
+void standardize_columns(cudaStream_t s, const T* X_in, T* X_out, i64 n, i64 p, i64 ld, int flag,
+                         T* meanX, T* scaleX, T* tmp);
+// y: device vector, in place.  out2 (device): {meanY, scaleY}; tmp: 2 scratch entries
+template <class T> void standardize_y(cudaStream_t s, T* y, i64 n, int flag, T* out2, T* tmp);
+// column sums / sums of squared deviations for row-sharded standardisation
+template <class T> void column_sums(cudaStream_t s, const T* X, i64 n, i64 p, i64 ld, T* sums);
+template <class T> void column_center_sumsq(cudaStream_t s, T* X, i64 n, i64 p, i64 ld, const T* mean, T* sumsq, bool center_in_place);
+template <class T> void column_scale(cudaStream_t s, T* X, i64 n, i64 p, i64 ld, const T* inv_scale);
+void convert_f64_to_f32(cudaStream_t s, const double* in, float* out, size_t count);
+
+// ---- chol.cu -----------------------------------------------------------------------------
+// In-place lower Cholesky of the p x p matrix A (column-major, lda); `work` >= chol_work(p).
+// Also leaves the inverses of the diagonal blocks in `work` for spd_inverse.
+// info (device int): 0 ok, k > 0: pivot k not positive.
+template <class T> size_t chol_work(i64 p);
+template <class T> void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev);
+// W (p x p, zero-initialised by the callee) <- L^-1 given the factor in A and chol's `work`
+template <class T> void tri_inverse_lower(cudaStream_t s, const T* L, i64 p, i64 lda, const T* work, T* W, i64 ldw, T* tmp);
+// Kinv (p x p, full symmetric) <- W' W
+template <class T> void gram_of_lower(cudaStream_t s, const T* W, i64 p, i64 ldw, T* Kinv, i64 ldk);
+// solve L L' x = b in place for one right-hand side (LAD's get_x; not on the per-iteration path)
+template <class T> void chol_solve_vec(cudaStream_t s, const T* L, i64 p, i64 lda, T* b);
+
+// ---- fadmm_tall.cu : the persistent lambda-path kernel (lasso / enet, n > p) ---------------
+struct TallPathArgs {
+    const float* Kinv;      // p x p, full symmetric inverse of X'X + rho I
+    const float* XY;        // p
+    const double* lambdas;  // nl, internal scale (lambda * n / scaleY)
+    int nl;
+    int p;
+    int maxit;
+    double eps_abs, eps_rel, rho;
+    int enet;
+    double alpha;
+    float* state;           // workspace, tall_state_floats(p) floats, zeroed by the caller for a cold start
+    float* z_out;           // nl x p  (row k = z at lambda k, standardised scale)
+    int* niter_out;         // nl
+    double* trace;          // optional: rows of 5 doubles for lambda `trace_lambda`
+    int trace_cap;
+    int trace_lambda;
+    int* trace_rows;        // device int
+    unsigned long long* barrier;   // device counter, zeroed
+    int snake;              // alternate the row sweep direction every iteration (L2 reuse)
+};
+size_t tall_state_floats(int p);
+// returns the grid size used
+int launch_tall_path(cudaStream_t s, const TallPathArgs& a);
+
+// stand-alone fused z+u+residual pass (the K8 micro-benchmark of SURVEY.md section 8d)
+void fused_zu_pass(cudaStream_t s, const float* x, const float* adj_y, const float* old_z, const float* adj_z,
+                   float* z, float* y, i64 len, double lambda, double rho, int enet, double alpha,
+                   double* sums_dev /* 6 */, float* partial_work /* >= 6 * fused_zu_blocks() */);
+int fused_zu_blocks();
+
+// ---- synth.cu ----------------------------------------------------------------------------
+void synth_design_f32(cudaStream_t s, float* X, float* y, i64 nrows, i64 p, i64 row0, uint64_t seed,
+                      float mean_x, float sd_x, int nsig, float noise);
+
+}  // namespace b200

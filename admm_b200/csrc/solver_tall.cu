@@ -1,0 +1,266 @@
+// solver_tall.cu -- host driver of admm_lasso / admm_enet for n > p.
+//
+// Restates /root/reference/src/Lasso.cpp:39-135 (and Enet.cpp) around the device kernels:
+//   ingest (f64 -> f32)            Lasso.cpp:45-50
+//   DataStd::standardize           Lasso.cpp:67-68  -> stdize.cu
+//   ADMMLassoTall ctor: X'y        ADMMLassoTall.h:164-174 -> gemv_t
+//   lambda grid                    Lasso.cpp:78-89
+//   init(): Gram, coarse rho, +rho I, LLT      ADMMLassoTall.h:179-216 -> gram / coarse_eig / chol
+//   lambda loop with warm starts   Lasso.cpp:97-124 -> ONE launch of the persistent path kernel
+//   recover + write_beta_matrix    Lasso.cpp:108-111
+//
+// With a communicator installed (b200admm_comm_init) `d` is this rank's row block: column sums,
+// sums of squares, X'y and the Gram matrix are all-reduced (sum) over NVLink, after which every
+// rank holds bit-identical K^-1 and runs the identical iteration -- the serial algorithm of the
+// reference, with its O(n p^2) setup split across GPUs.
+#include "solvers.h"
+#include "kernels.h"
+#include "comm.h"
+#include <cmath>
+#include <cstring>
+
+namespace b200 {
+
+namespace {
+
+// DataStd over row shards (a world of one rank degenerates to the plain single-GPU passes).
+// y_dev in place; X_in -> X_out (may alias).  Returns meanY / scaleY on the host.
+struct StdStats {
+    std::vector<float> meanX, scaleX;
+    float meanY = 0.f, scaleY = 1.f;
+};
+
+void standardize_all(cudaStream_t s, const float* X_in, float* X_out, float* y, i64 n_local, i64 n_total, i64 p,
+                     int flag, float* d_meanX, float* d_scaleX, StdStats& st)
+{
+    DevBuf<float> tmp(2 * p + 8);
+    float* sums = tmp.p;
+    float* inv = tmp.p + p;
+    float* ys = tmp.p + 2 * p;          // [0] sum / mean, [1] sumsq / scale
+    // ---- y
+    if (flag != 0) {
+        column_sums<float>(s, y, n_local, 1, n_local, ys);
+        allreduce_sum(s, ys, 1);
+        mean_from_sums<float>(s, ys, 1, n_total, ys);                       // ys[0] = mean(y)
+        column_center_sumsq<float>(s, y, n_local, 1, n_local, ys, ys + 1, false);
+        allreduce_sum(s, ys + 1, 1);
+        if (flag == 1) {
+            scale_from_sumsq<float>(s, ys + 1, 1, n_total, true, ys + 1, nullptr);
+            column_apply<float>(s, y, y, n_local, 1, n_local, nullptr, nullptr, ys + 1);   // y /= scaleY (not centred)
+        } else {
+            scale_from_sumsq<float>(s, ys + 1, 1, n_total, false, ys + 1, nullptr);
+            column_apply<float>(s, y, y, n_local, 1, n_local, ys, nullptr, ys + 1);        // (y - mean) / scaleY
+        }
+        float h[2];
+        CUDA_CHECK(cudaMemcpyAsync(h, ys, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        st.meanY = (flag == 1) ? 0.f : h[0];
+        st.scaleY = h[1];
+    }
+    // ---- X
+    st.meanX.assign(p, 0.f);
+    st.scaleX.assign(p, 1.f);
+    switch (flag) {
+    case 1:
+        column_sums<float>(s, X_in, n_local, p, n_local, sums);
+        allreduce_sum(s, sums, p);
+        mean_from_sums<float>(s, sums, p, n_total, sums);
+        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, n_local, sums, d_scaleX, false);
+        allreduce_sum(s, d_scaleX, p);
+        scale_from_sumsq<float>(s, d_scaleX, p, n_total, true, d_scaleX, inv);
+        column_apply<float>(s, X_in, X_out, n_local, p, n_local, nullptr, inv, nullptr);
+        break;
+    case 2:
+        column_sums<float>(s, X_in, n_local, p, n_local, sums);
+        allreduce_sum(s, sums, p);
+        mean_from_sums<float>(s, sums, p, n_total, d_meanX);
+        column_apply<float>(s, X_in, X_out, n_local, p, n_local, d_meanX, nullptr, nullptr);
+        break;
+    case 3:
+        column_sums<float>(s, X_in, n_local, p, n_local, sums);
+        allreduce_sum(s, sums, p);
+        mean_from_sums<float>(s, sums, p, n_total, d_meanX);
+        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, n_local, d_meanX, d_scaleX, false);
+        allreduce_sum(s, d_scaleX, p);
+        scale_from_sumsq<float>(s, d_scaleX, p, n_total, false, d_scaleX, inv);
+        column_apply<float>(s, X_in, X_out, n_local, p, n_local, d_meanX, inv, nullptr);
+        break;
+    default:
+        if (X_in != X_out) column_apply<float>(s, X_in, X_out, n_local, p, n_local, nullptr, nullptr, nullptr);
+        break;
+    }
+    if (flag == 2 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.meanX.data(), d_meanX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (flag == 1 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.scaleX.data(), d_scaleX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+}  // namespace
+
+void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
+                       const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out)
+{
+    std::vector<std::vector<float>> cols(nl);
+    std::vector<float> beta0(nl, 0.f);
+    for (int k = 0; k < nl; k++) {
+        cols[k].assign(z_all.begin() + (size_t)k * p, z_all.begin() + (size_t)(k + 1) * p);
+        beta0[k] = recover_sparse<float>(flag, cols[k], meanX, scaleX, meanY, scaleY);
+    }
+    assemble_csc<float>(cols, beta0, true, p, out);
+}
+
+void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
+{
+    const b200admm_data* d = rq.d;
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    Comm& cm = comm();
+    const i64 n_local = d->n, p = d->p;
+    const i64 n = cm.active() ? (i64)std::llround(allreduce_sum_host(s, (double)n_local)) : n_local;
+    if (!(n > p)) {
+        if (cm.active()) throw ArgError("row-sharded lasso needs n > p (the wide solver is not sharded)");
+        solve_wide(rq, out);
+        return;
+    }
+    if (d->dtype == B200ADMM_F64_DEVICE) throw ArgError("lasso / enet compute in float32: pass f64 host, f32 host or f32 device data");
+    const double t_begin = wall_now();
+    const int flag = (rq.standardize ? 1 : 0) + (rq.intercept ? 2 : 0);
+    const i64 ld = (p + 3) & ~(i64)3;
+    EventTimer tm(s);
+    b200admm_timing T;
+    memset(&T, 0, sizeof T);
+
+    // ---- ingest ------------------------------------------------------------------------------
+    DevBuf<float> Xs((size_t)n_local * (size_t)p), ys(n_local);
+    const float* X_in = Xs.p;
+    tm.start();
+    if (d->dtype == B200ADMM_F32_DEVICE) {
+        X_in = (const float*)d->x;                      // standardised out of place, caller's copy untouched
+        CUDA_CHECK(cudaMemcpyAsync(ys.p, d->y, n_local * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+        ingest_f32(s, d->x, d->dtype, (size_t)n_local * (size_t)p, Xs.p);
+        ingest_f32(s, d->y, d->dtype, (size_t)n_local, ys.p);
+    }
+    T.ingest = tm.stop();
+
+    // ---- DataStd -----------------------------------------------------------------------------
+    DevBuf<float> d_meanX(p), d_scaleX(p);
+    StdStats st;
+    tm.start();
+    standardize_all(s, X_in, Xs.p, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    T.standardize = tm.stop();
+
+    // ---- X'y, lambda0, Gram ------------------------------------------------------------------
+    DevBuf<float> XY(ld);
+    DevBuf<float> G((size_t)p * (size_t)ld);
+    tm.start();
+    XY.zero(s);
+    gemv_t<float>(s, Xs.p, n_local, p, n_local, ys.p, XY.p);
+    allreduce_sum(s, XY.p, p);
+    G.zero(s);
+    const bool on_tensor = (ld == p) && gram_tn_tensor(s, Xs.p, n_local, p, G.p);
+    if (!on_tensor) {
+        // CUDA-core path (shapes the tensor kernel does not take)
+        gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, n_local, Xs.p, n_local, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
+    }
+    allreduce_sum(s, G.p, (size_t)p * (size_t)ld);
+    std::vector<float> h_xy(p);
+    CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), XY.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    T.gram = tm.stop();
+    Xs.release();                                       // the tall solver never touches X again
+    ys.release();
+
+    float lambda0 = 0.f;
+    for (i64 j = 0; j < p; j++) lambda0 = std::max(lambda0, std::fabs(h_xy[j]));
+    if (rq.enet) lambda0 = (float)((double)lambda0 / ((double)(float)rq.alpha + 0.0001));   // ADMMEnet.h:56
+
+    // ---- lambda sequence (Lasso.cpp:78-89) -----------------------------------------------------
+    std::vector<double> lam;
+    if (rq.nlambda_given < 1) {
+        if (rq.nlambda < 1) throw ArgError("nlambda must be at least 1");
+        const double lmax = (double)lambda0 / (double)n * (double)st.scaleY;
+        make_lambda_grid(lmax, rq.lmin_ratio, rq.nlambda, lam);
+    } else {
+        if (!rq.lambda_given) throw ArgError("lambda is null");
+        lam.assign(rq.lambda_given, rq.lambda_given + rq.nlambda_given);
+    }
+    const int nl = (int)lam.size();
+    std::vector<double> ilam(nl);
+    for (int k = 0; k < nl; k++) ilam[k] = lam[k] * (double)n / (double)st.scaleY;           // Lasso.cpp:99
+
+    // ---- rho (ADMMLassoTall.h:194-202) ---------------------------------------------------------
+    double rho = rq.opts.rho;
+    double ev = 0.0;
+    tm.start();
+    if (rho <= 0) {
+        const float evf = coarse_eig_device(s, G.p, p, ld, nullptr);
+        ev = (double)evf;
+        const float lambda_f = (float)ilam[0];
+        rho = std::pow((double)evf, 1.0 / 3) * std::pow((double)lambda_f, 2.0 / 3);
+    }
+    T.eig = tm.stop();
+
+    // ---- K^-1 = (X'X + rho I)^-1  (replaces LLT::compute, ADMMLassoTall.h:204-205) --------------
+    tm.start();
+    add_to_diagonal(s, G.p, ld, p, (float)rho);
+    {
+        DevBuf<float> W((size_t)p * (size_t)ld);
+        int info = 0;
+        spd_inverse_f32(s, G.p, p, ld, W.p, &info);
+    }
+    T.factor = tm.stop();
+
+    // ---- the lambda path: one persistent kernel ------------------------------------------------
+    DevBuf<float> state(tall_state_floats((int)p));
+    DevBuf<float> z_out((size_t)nl * (size_t)p);
+    DevBuf<int> niter_dev(nl), trace_rows(1);
+    DevBuf<double> lam_dev(nl);
+    DevBuf<unsigned long long> barrier(1);
+    TraceRequest& tr = trace_request();
+    DevBuf<double> trace_dev;
+    const bool tracing = tr.buf && tr.cap > 0 && tr.which >= 0 && tr.which < nl;
+    if (tracing) trace_dev.alloc((size_t)5 * tr.cap);
+
+    state.zero(s);
+    barrier.zero(s);
+    trace_rows.zero(s);
+    CUDA_CHECK(cudaMemcpyAsync(lam_dev.p, ilam.data(), nl * sizeof(double), cudaMemcpyHostToDevice, s));
+
+    TallPathArgs a;
+    a.Kinv = G.p; a.XY = XY.p; a.lambdas = lam_dev.p; a.nl = nl; a.p = (int)p; a.maxit = rq.opts.maxit;
+    a.eps_abs = rq.opts.eps_abs; a.eps_rel = rq.opts.eps_rel; a.rho = rho;
+    a.enet = rq.enet ? 1 : 0; a.alpha = rq.alpha;
+    a.state = state.p; a.z_out = z_out.p; a.niter_out = niter_dev.p;
+    a.trace = tracing ? trace_dev.p : nullptr; a.trace_cap = tracing ? tr.cap : 0; a.trace_lambda = tracing ? tr.which : -1;
+    a.trace_rows = trace_rows.p; a.barrier = barrier.p;
+    const char* snake_env = getenv("B200ADMM_SNAKE");
+    a.snake = snake_env ? atoi(snake_env) : 1;
+    tm.start();
+    launch_tall_path(s, a);
+    T.iterate = tm.stop();
+
+    // ---- results --------------------------------------------------------------------------------
+    tm.start();
+    std::vector<float> z_all((size_t)nl * (size_t)p);
+    out->niter = (int*)malloc(sizeof(int) * nl);
+    out->lambda = (double*)malloc(sizeof(double) * nl);
+    if (!out->niter || !out->lambda) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
+    CUDA_CHECK(cudaMemcpyAsync(z_all.data(), z_out.p, z_all.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(out->niter, niter_dev.p, nl * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (tracing) {
+        int rows = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&rows, trace_rows.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        rows = std::min(rows, tr.cap);
+        CUDA_CHECK(cudaMemcpyAsync(tr.buf, trace_dev.p, (size_t)5 * rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (tr.nrows) *tr.nrows = rows;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int k = 0; k < nl; k++) out->lambda[k] = lam[k];
+    out->nlambda = nl;
+    finish_lasso_path(z_all, nl, p, flag, st.meanX, st.scaleX, st.meanY, st.scaleY, out);
+    T.finish = tm.stop();
+    T.total = wall_now() - t_begin;
+    out->rho = rho; out->eig = ev; out->lambda0 = lambda0; out->t = T;
+}
+
+}  // namespace b200

@@ -1,0 +1,181 @@
+"""GPU unit tests of the individual CUDA kernels behind the C ABI (b200admm_k_* entry points),
+each against a float64 NumPy statement of the same operation or against the CPU oracle.
+Floating-point tolerances are stated per test; integer/index outputs must match exactly."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from admm_b200 import _capi
+    _capi.device_info()
+    return _capi
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def colmajor_dev(torch, a):
+    """numpy (n, p) -> CUDA tensor holding the column-major image (a contiguous (p, n) tensor)."""
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+
+
+def back(t):
+    return t.cpu().numpy().T
+
+
+@pytest.mark.parametrize("n,p", [(1000, 64), (777, 33), (4096, 5), (65, 130)])
+@pytest.mark.parametrize("flags", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_standardize_matches_oracle(K, torch, n, p, flags):
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(n * p)
+    x = rng.normal(1.2, 2.0, size=(n, p)).astype(np.float32)
+    y = (rng.normal(size=n) + 5).astype(np.float32)
+    xd, yd = colmajor_dev(torch, x), torch.from_numpy(y.copy()).cuda()
+    out = torch.empty_like(xd)
+    meanx = np.zeros(p, np.float32); scalex = np.ones(p, np.float32); ys = np.zeros(2, np.float32)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_standardize_f32(xd.data_ptr(), out.data_ptr(), yd.data_ptr(), n, p, flags[0], flags[1],
+                                               meanx.ctypes.data, scalex.ctypes.data, ys.ctypes.data))
+    xo = np.asfortranarray(x.copy()); yo = y.copy()
+    st = O.standardize_f32(xo, yo, standardize=bool(flags[0]), intercept=bool(flags[1]))
+    # float32 data, sums taken in a different order: a few ulp
+    assert np.allclose(back(out), xo, rtol=2e-5, atol=2e-6)
+    assert np.allclose(yd.cpu().numpy(), yo, rtol=2e-5, atol=2e-6)
+    if flags[1]:
+        assert np.allclose(meanx, st["meanX"], rtol=1e-5, atol=1e-6)
+        assert abs(ys[0] - st["meanY"]) < 1e-5 * max(1, abs(st["meanY"]))
+    if flags[0]:
+        assert np.allclose(scalex, st["scaleX"], rtol=1e-5)
+    if flags[0] or flags[1]:
+        assert abs(ys[1] - st["scaleY"]) < 1e-5 * st["scaleY"]
+    assert np.array_equal(back(xd), x)          # input untouched (out-of-place)
+
+
+@pytest.mark.parametrize("n,p", [(5000, 128), (1234, 77), (300, 300), (20000, 260)])
+def test_gram_cuda_cores(K, torch, n, p):
+    rng = np.random.default_rng(n + p)
+    x = rng.normal(size=(n, p)).astype(np.float32)
+    xd = colmajor_dev(torch, x)
+    g = torch.zeros(p, p, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_gram_f32(xd.data_ptr(), n, p, g.data_ptr(), 0))
+    ref = x.astype(np.float64).T @ x.astype(np.float64)
+    got = g.cpu().numpy()
+    assert np.array_equal(got, got.T)                                   # exactly symmetric (mirrored store)
+    # float32 accumulation of n terms: error ~ sqrt(n) * eps * |x_i||x_j|
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert (np.abs(got - ref) / scale).max() < 3e-6 * max(1.0, np.sqrt(n / 1000.0))
+
+
+def test_gemv_t(K, torch):
+    rng = np.random.default_rng(4)
+    for m, nc in [(100000, 7), (1000, 1000), (37, 5), (40001, 3)]:
+        a = rng.normal(size=(m, nc)).astype(np.float32)
+        v = rng.normal(size=m).astype(np.float32)
+        ad, vd = colmajor_dev(torch, a), torch.from_numpy(v).cuda()
+        out = torch.zeros(nc, device="cuda", dtype=torch.float32)
+        torch.cuda.synchronize()
+        K.check(K.lib().b200admm_k_gemv_t_f32(ad.data_ptr(), m, nc, vd.data_ptr(), out.data_ptr()))
+        ref = a.astype(np.float64).T @ v.astype(np.float64)
+        assert np.abs(out.cpu().numpy() - ref).max() < 2e-6 * np.sqrt(m) * 3
+
+
+@pytest.mark.parametrize("p", [64, 128, 129, 500, 1000])
+def test_cholesky_and_spd_inverse(K, torch, p):
+    rng = np.random.default_rng(p)
+    x = rng.normal(size=(4 * p, p))
+    a = (x.T @ x + 5.0 * np.eye(p)).astype(np.float32)
+    ad = torch.from_numpy(a.copy()).cuda()               # symmetric: row/column major coincide
+    info = C.c_int(-1)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_chol_f32(ad.data_ptr(), p, C.byref(info)))
+    assert info.value == 0
+    L = np.tril(back(ad)).astype(np.float64)
+    a64 = a.astype(np.float64)
+    assert np.abs(L @ L.T - a64).max() / np.abs(a64).max() < 5e-6      # backward error of a float32 factorisation
+    # explicit inverse
+    ad2 = torch.from_numpy(a.copy()).cuda()
+    work = torch.empty(p, p, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_spd_inverse_f32(ad2.data_ptr(), p, work.data_ptr(), C.byref(info)))
+    inv = ad2.cpu().numpy().astype(np.float64)
+    assert np.array_equal(inv, inv.T)
+    cond = np.linalg.cond(a64)
+    assert np.abs(inv @ a64 - np.eye(p)).max() < 2e-6 * cond * 4
+
+
+def test_cholesky_reports_indefinite(K, torch):
+    p = 200
+    a = np.eye(p, dtype=np.float32)
+    a[150, 150] = -1.0
+    ad = torch.from_numpy(a).cuda()
+    info = C.c_int(0)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_chol_f32(ad.data_ptr(), p, C.byref(info)))
+    assert info.value == 151
+
+
+def numpy_fused_zu(x, adj_y, old_z, adj_z, lam, rho, enet, alpha):
+    """float32 restatement of ADMMLassoTall::next_z / next_residual + FADMMBase::update_y."""
+    f = np.float32
+    frho = f(rho)
+    v = (x + adj_y / frho).astype(f)
+    pen = float(f(lam)) / rho
+    if not enet:
+        vd = v.astype(np.float64)
+        z = np.where(vd > pen, vd - pen, np.where(vd < -pen, vd + pen, 0.0)).astype(f)
+    else:
+        th = f(float(f(alpha)) * pen)
+        den = f(1.0 + pen * (1.0 - float(f(alpha))))
+        z = np.where(v > th, (v - th) / den, np.where(v < -th, (v + th) / den, f(0))).astype(f)
+    r = (x - z).astype(f)
+    y = (adj_y + frho * r).astype(f)
+    d = lambda a: float(np.sum(a.astype(np.float64) ** 2))
+    return z, y, [d(r), d(z - old_z), d(z - adj_z), d(x), d(z), d(y)]
+
+
+@pytest.mark.parametrize("enet", [0, 1])
+@pytest.mark.parametrize("length", [1 << 20, 1000003, 5])
+def test_fused_zu_kernel(K, torch, enet, length):
+    rng = np.random.default_rng(length + enet)
+    x, ay, oz, az = (rng.normal(size=length).astype(np.float32) for _ in range(4))
+    oz[rng.uniform(size=length) < 0.5] = 0
+    dev = [torch.from_numpy(a).cuda() for a in (x, ay, oz, az)]
+    z = torch.empty(length, device="cuda", dtype=torch.float32)
+    y = torch.empty(length, device="cuda", dtype=torch.float32)
+    sums = np.zeros(6)
+    ms = C.c_float(0)
+    lam, rho, alpha = 0.7, 1.3, 0.4
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_fused_zu_f32(*(t.data_ptr() for t in dev), z.data_ptr(), y.data_ptr(), length,
+                                            lam, rho, enet, alpha, sums.ctypes.data, C.byref(ms), 1))
+    zr, yr, sr = numpy_fused_zu(x, ay, oz, az, lam, rho, enet, alpha)
+    assert np.array_equal(z.cpu().numpy(), zr)        # element-wise part is bit-exact
+    assert np.array_equal(y.cpu().numpy(), yr)
+    assert np.allclose(sums, sr, rtol=2e-5)           # float32 partial sums, different order
+
+
+def test_synth_design_statistics_and_sharding(K, torch):
+    n, p = 40000, 64
+    x = torch.empty(p, n, device="cuda", dtype=torch.float32)
+    y = torch.empty(n, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_synth_f32(x.data_ptr(), y.data_ptr(), n, p, 0, 123, 0.0, 2.0, 10, 1.0))
+    xa = x.cpu().numpy()
+    assert abs(xa.mean()) < 0.02 and abs(xa.std() - 2.0) < 0.02
+    assert abs(np.corrcoef(xa[0], xa[1])[0, 1]) < 0.03
+    # a row block generated on its own is the same rows of the same global matrix
+    r0, nr = 10001, 5003
+    xs = torch.empty(p, nr, device="cuda", dtype=torch.float32)
+    ys = torch.empty(nr, device="cuda", dtype=torch.float32)
+    K.check(K.lib().b200admm_synth_f32(xs.data_ptr(), ys.data_ptr(), nr, p, r0, 123, 0.0, 2.0, 10, 1.0))
+    assert np.array_equal(xs.cpu().numpy(), xa[:, r0:r0 + nr])
+    assert np.array_equal(ys.cpu().numpy(), y.cpu().numpy()[r0:r0 + nr])

@@ -1,0 +1,182 @@
+"""GPU parity tests of the tall (n > p) lasso / elastic-net path: the CUDA library, called through
+its C ABI (via the Python mirror of the R chain), against the CPU oracle on the same inputs and
+against the reference's README vectors.
+
+Tolerances (stated): float32 path, same (X, y, lambda, rho):
+  * coefficients: max|dbeta| <= 1e-4 * max(1, |beta|_inf) on the original scale (the solver's own
+    stopping tolerance is 1e-5 relative on standardised variables; GPU and CPU differ only in
+    the summation order of the norms / K^-1 product, but an iteration more or less moves beta
+    by about the stopping tolerance);
+  * support identical except coordinates whose magnitude is below 1e-4 in either solution;
+  * per-iteration scalars (eps, residuals) within 1e-3 relative over the first iterations;
+  * iteration counts within +-2 per lambda or 3 % in total.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import readme_vectors as R
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LAM = float(np.exp(-2))
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.fixture(scope="module")
+def A():
+    import admm_b200
+    admm_b200.device_info()
+    return admm_b200
+
+
+@pytest.fixture(scope="module")
+def lasso_xy():
+    d = np.load(os.path.join(G, "readme_lasso_data.npz"))
+    return d["x"], d["y"]
+
+
+def dense(beta):
+    return np.asarray(beta.todense())
+
+
+def assert_beta_close(b_gpu, b_cpu, tol=1e-4, band=1e-4):
+    scale = max(1.0, float(np.abs(b_cpu).max()))
+    assert np.abs(b_gpu - b_cpu).max() <= tol * scale, np.abs(b_gpu - b_cpu).max()
+    mism = (b_gpu != 0) != (b_cpu != 0)
+    if mism.any():
+        assert max(np.abs(b_gpu[mism]).max(), np.abs(b_cpu[mism]).max()) < band
+
+
+def test_readme_lasso(A, O, lasso_xy):
+    x, y = lasso_xy
+    f = A.admm_lasso(x, y).penalty(LAM).fit()
+    o = O.lasso_path(x, y, [LAM])
+    b = dense(f.beta)[:, 0]
+    assert np.array_equal(b != 0, R.LASSO_ADMM != 0)                  # support bit-exact vs the reference's README
+    assert np.abs(b - R.LASSO_ADMM).max() < 2e-5
+    assert np.abs(b - o["beta"][:, 0]).max() < 5e-6
+    assert abs(int(f.niter[0]) - int(o["niter"][0])) <= 1
+    assert abs(f.info["rho"] - o["rho"]) < 1e-5 * o["rho"]
+
+
+def test_readme_enet(A, O, lasso_xy):
+    x, y = lasso_xy
+    f = A.admm_enet(x, y).penalty(LAM, alpha=0.5).fit()
+    o = O.lasso_path(x, y, [LAM], model="enet", alpha=0.5)
+    b = dense(f.beta)[:, 0]
+    assert np.array_equal(b != 0, R.ENET_ADMM != 0)
+    assert np.abs(b - R.ENET_ADMM).max() < 5e-6
+    assert np.abs(b - o["beta"][:, 0]).max() < 5e-6
+    assert abs(int(f.niter[0]) - int(o["niter"][0])) <= 1
+
+
+def make_problem(n, p, seed, nsig=10, mean=0.0):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(mean, 2.0, size=(n, p))
+    b = np.zeros(p)
+    b[:nsig] = rng.uniform(size=nsig)
+    y = x @ b + rng.normal(size=n)
+    return np.asfortranarray(x), y
+
+
+@pytest.mark.parametrize("n,p,model,alpha", [(2000, 200, "lasso", 1.0), (1501, 137, "lasso", 1.0),
+                                             (3000, 256, "enet", 0.5), (400, 50, "enet", 0.3)])
+def test_path_matches_oracle(A, O, n, p, model, alpha):
+    x, y = make_problem(n, p, seed=n + p)
+    nl = 25
+    if model == "lasso":
+        f = A.admm_lasso(x, y).penalty(nlambda=nl).fit()
+    else:
+        f = A.admm_enet(x, y).penalty(nlambda=nl, alpha=alpha).fit()
+    o = O.lasso_path(x, y, nlambda=nl, model=model, alpha=alpha)
+    assert np.allclose(f.lambda_, o["lambda_"], rtol=1e-5)
+    assert abs(f.info["rho"] - o["rho"]) < 1e-4 * o["rho"]
+    bg, bc = dense(f.beta), o["beta"]
+    for k in range(nl):
+        assert_beta_close(bg[:, k], bc[:, k])
+    ng, nc = f.niter.astype(int), o["niter"].astype(int)
+    assert abs(ng.sum() - nc.sum()) <= max(3, 0.03 * nc.sum()), (ng, nc)
+    assert np.abs(ng - nc).max() <= max(2, 0.1 * nc.max()), (ng, nc)
+
+
+@pytest.mark.parametrize("standardize,intercept", [(True, True), (True, False), (False, True), (False, False)])
+def test_standardize_flags(A, O, standardize, intercept):
+    x, y = make_problem(500, 40, seed=11, mean=1.2)
+    y = y + 5.0
+    lam = [0.5, 0.1, 0.02]
+    f = A.admm_lasso(x, y, intercept=intercept, standardize=standardize).penalty(lam).fit()
+    o = O.lasso_path(x, y, lam, standardize=standardize, intercept=intercept)
+    bg, bc = dense(f.beta), o["beta"]
+    for k in range(len(lam)):
+        assert_beta_close(bg[:, k], bc[:, k], tol=2e-4)
+    if not intercept:
+        assert np.all(bg[0] == 0)
+
+
+def test_iteration_trace_matches_oracle(A, O):
+    from admm_b200 import _capi as K
+    x, y = make_problem(1200, 96, seed=5)
+    lam = [0.05]
+    with K.trace(which=0, cap=4000) as tr:
+        f = A.admm_lasso(x, y).penalty(lam).fit()
+    o = O.lasso_path(x, y, lam, trace_lambda=0, trace_cap=4000)
+    tg, tc = tr.rows, o["trace"][: int(o["niter"][0])]
+    m = min(len(tg), len(tc), 15)
+    assert m >= 5
+    # eps_primal, resid_primal, eps_dual, resid_dual, rho
+    assert np.allclose(tg[:m], tc[:m], rtol=1e-3, atol=1e-7), np.abs(tg[:m] / tc[:m] - 1).max()
+    assert len(tg) == int(f.niter[0])
+
+
+def test_input_dtypes_agree(A):
+    import torch
+    x, y = make_problem(800, 64, seed=3)
+    f64 = A.admm_lasso(x, y).penalty(nlambda=5).fit()
+    x32 = np.asfortranarray(x.astype(np.float32))
+    y32 = y.astype(np.float32)
+    f32 = A.admm_lasso(x32, y32).penalty(nlambda=5).fit()
+    xd = torch.from_numpy(np.ascontiguousarray(x32.T)).cuda().t()      # column-major on the device
+    yd = torch.from_numpy(y32).cuda()
+    fd = A.admm_lasso(xd, yd).penalty(nlambda=5).fit()
+    assert np.array_equal(f64.beta.toarray(), f32.beta.toarray())      # same float32 data after the narrowing copy
+    assert np.array_equal(f32.beta.toarray(), fd.beta.toarray())
+    assert np.array_equal(xd.t().cpu().numpy(), np.ascontiguousarray(x32.T))  # caller's device copy untouched
+
+
+def test_user_rho_and_nonconvergence(A, O):
+    x, y = make_problem(600, 30, seed=9)
+    f = A.admm_lasso(x, y).penalty([0.1]).opts(maxit=3, rho=50.0).fit()
+    o = O.lasso_path(x, y, [0.1], maxit=3, rho=50.0)
+    assert int(f.niter[0]) == 4 == int(o["niter"][0])                   # maxit + 1 (FADMMBase.h:264)
+    assert np.abs(dense(f.beta)[:, 0] - o["beta"][:, 0]).max() < 1e-5
+
+
+def test_too_few_variables_is_an_error(A):
+    from admm_b200 import B200AdmmError
+    x, y = make_problem(50, 2, seed=1, nsig=1)
+    with pytest.raises(B200AdmmError) as e:
+        A.admm_lasso(x, y).penalty([0.1]).fit()
+    assert e.value.code == -5
+
+
+def test_kkt_at_moderate_size(A):
+    """Size-independent property: the solution satisfies the lasso optimality conditions
+    |X_j'(y - X b)| <= n*lambda (+tol), with equality and matching sign on the support."""
+    n, p = 20000, 500
+    x, y = make_problem(n, p, seed=21, nsig=20)
+    lam = 0.05
+    f = A.admm_lasso(x, y, standardize=False, intercept=False).penalty([lam]).opts(eps_abs=1e-7, eps_rel=1e-7).fit()
+    b = dense(f.beta)[1:, 0]
+    g = x.T @ (y - x @ b) / n
+    assert np.abs(g).max() <= lam * (1 + 2e-3)
+    s = b != 0
+    assert s.sum() >= 15
+    assert np.allclose(g[s], lam * np.sign(b[s]), rtol=5e-3)
