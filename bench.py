@@ -315,7 +315,8 @@ def main():
                            "h2d_bytes_per_step": int(4 * n_local * p + 4 * n_local),
                            "d2h_bytes_per_step": int(4 * nl * p + 4 * nl + 3 * 4 * p + 8),
                            "path_wall_s": e_wall / args.e2e_steps, "steps": args.e2e_steps,
-                           "ingest_s": float(np.mean([f.info["timing"]["ingest"] for f in fh])),
+                           "device_s_per_step": e_dev / args.e2e_steps,
+                           "phase_s": {k: float(np.mean([f.info["timing"][k] for f in fh])) for k in fh[-1].info["timing"]},
                            "input": "float32 column-major, pinned host memory"}
             del Xh, yh
         except Exception as ex:  # pinned allocation can fail on small hosts: say so, do not fake a number
