@@ -461,8 +461,9 @@ int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g, int use_te
         Context& c = ctx();
         bool done = false;
         if (use_tensor) {
-            done = gram_tn_tensor(c.stream, (const float*)x, n, p, (float*)g);
-            if (!done && use_tensor > 1) throw ArgError("tensor-core Gram kernel cannot take this shape");
+            CUDA_CHECK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)p * (size_t)p, c.stream));
+            done = gram_tn_tensor(c.stream, (const float*)x, n, p, (float*)g, p, use_tensor > 1 ? 1 : 0);
+            if (!done) throw ArgError("tensor-core Gram kernel cannot take this shape (needs n % 4 == 0, n >= 16, p >= 8)");
         }
         if (!done)
             gemm<float>(c.stream, true, false, p, p, n, 1.f, (const float*)x, n, (const float*)x, n, 0.f, (float*)g, p, GEMM_LOWER | GEMM_MIRROR);

@@ -18,8 +18,11 @@ void gemm(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const 
           const T* B, i64 ldb, T beta, T* C, i64 ldc, int mode);
 
 // ---- gram_tc.cu : X'X on the tcgen05 tensor cores (3xTF32 split, fp32-accurate) ------------
+// G (p x p, leading dimension ld) must be zeroed by the caller; the full symmetric matrix is written.
+// exact_hi = 1 also rewrites the high parts in shared memory (does not rely on the tensor core
+// ignoring the 13 low mantissa bits of its fp32-typed operands).
 // returns false if the shape cannot use the tensor path (caller falls back to gemm<float>)
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 p, float* G /* p x p full */);
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 p, float* G, i64 ld, int exact_hi);
 
 // ---- gemv.cu -----------------------------------------------------------------------------
 // out[j] = sum_i A(i,j) v[i]   (A m x ncol column-major, lda)  -- one dot product per column

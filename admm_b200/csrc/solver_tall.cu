@@ -30,7 +30,7 @@ struct StdStats {
     float meanY = 0.f, scaleY = 1.f;
 };
 
-void standardize_all(cudaStream_t s, const float* X_in, float* X_out, float* y, i64 n_local, i64 n_total, i64 p,
+void standardize_all(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out, i64 ld_out, float* y, i64 n_local, i64 n_total, i64 p,
                      int flag, float* d_meanX, float* d_scaleX, StdStats& st)
 {
     DevBuf<float> tmp(2 * p + 8);
@@ -46,10 +46,10 @@ void standardize_all(cudaStream_t s, const float* X_in, float* X_out, float* y, 
         allreduce_sum(s, ys + 1, 1);
         if (flag == 1) {
             scale_from_sumsq<float>(s, ys + 1, 1, n_total, true, ys + 1, nullptr);
-            column_apply<float>(s, y, y, n_local, 1, n_local, nullptr, nullptr, ys + 1);   // y /= scaleY (not centred)
+            column_apply<float>(s, y, y, n_local, 1, n_local, n_local, nullptr, nullptr, ys + 1);   // y /= scaleY (not centred)
         } else {
             scale_from_sumsq<float>(s, ys + 1, 1, n_total, false, ys + 1, nullptr);
-            column_apply<float>(s, y, y, n_local, 1, n_local, ys, nullptr, ys + 1);        // (y - mean) / scaleY
+            column_apply<float>(s, y, y, n_local, 1, n_local, n_local, ys, nullptr, ys + 1);        // (y - mean) / scaleY
         }
         float h[2];
         CUDA_CHECK(cudaMemcpyAsync(h, ys, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -62,31 +62,31 @@ void standardize_all(cudaStream_t s, const float* X_in, float* X_out, float* y, 
     st.scaleX.assign(p, 1.f);
     switch (flag) {
     case 1:
-        column_sums<float>(s, X_in, n_local, p, n_local, sums);
+        column_sums<float>(s, X_in, n_local, p, ld_in, sums);
         allreduce_sum(s, sums, p);
         mean_from_sums<float>(s, sums, p, n_total, sums);
-        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, n_local, sums, d_scaleX, false);
+        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, ld_in, sums, d_scaleX, false);
         allreduce_sum(s, d_scaleX, p);
         scale_from_sumsq<float>(s, d_scaleX, p, n_total, true, d_scaleX, inv);
-        column_apply<float>(s, X_in, X_out, n_local, p, n_local, nullptr, inv, nullptr);
+        column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, nullptr, inv, nullptr);
         break;
     case 2:
-        column_sums<float>(s, X_in, n_local, p, n_local, sums);
+        column_sums<float>(s, X_in, n_local, p, ld_in, sums);
         allreduce_sum(s, sums, p);
         mean_from_sums<float>(s, sums, p, n_total, d_meanX);
-        column_apply<float>(s, X_in, X_out, n_local, p, n_local, d_meanX, nullptr, nullptr);
+        column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, d_meanX, nullptr, nullptr);
         break;
     case 3:
-        column_sums<float>(s, X_in, n_local, p, n_local, sums);
+        column_sums<float>(s, X_in, n_local, p, ld_in, sums);
         allreduce_sum(s, sums, p);
         mean_from_sums<float>(s, sums, p, n_total, d_meanX);
-        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, n_local, d_meanX, d_scaleX, false);
+        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, ld_in, d_meanX, d_scaleX, false);
         allreduce_sum(s, d_scaleX, p);
         scale_from_sumsq<float>(s, d_scaleX, p, n_total, false, d_scaleX, inv);
-        column_apply<float>(s, X_in, X_out, n_local, p, n_local, d_meanX, inv, nullptr);
+        column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, d_meanX, inv, nullptr);
         break;
     default:
-        if (X_in != X_out) column_apply<float>(s, X_in, X_out, n_local, p, n_local, nullptr, nullptr, nullptr);
+        if (X_in != X_out) column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, nullptr, nullptr, nullptr);
         break;
     }
     if (flag == 2 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.meanX.data(), d_meanX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -130,14 +130,23 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     memset(&T, 0, sizeof T);
 
     // ---- ingest ------------------------------------------------------------------------------
-    DevBuf<float> Xs((size_t)n_local * (size_t)p), ys(n_local);
+    // The standardised copy keeps a leading dimension that is a multiple of 4 (zero pad rows) so
+    // that the TMA descriptor of the tensor-core Gram kernel can address it for any n.
+    const i64 ldx = (n_local + 3) & ~(i64)3;
+    const bool padded = ldx != n_local;
+    DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
     const float* X_in = Xs.p;
+    i64 ld_in = ldx;
     tm.start();
+    if (padded) Xs.zero(s);
     if (d->dtype == B200ADMM_F32_DEVICE) {
         X_in = (const float*)d->x;                      // standardised out of place, caller's copy untouched
+        ld_in = n_local;
         CUDA_CHECK(cudaMemcpyAsync(ys.p, d->y, n_local * sizeof(float), cudaMemcpyDeviceToDevice, s));
     } else {
-        ingest_f32(s, d->x, d->dtype, (size_t)n_local * (size_t)p, Xs.p);
+        float* dst = Xs.p;
+        if (padded) { Xtmp.alloc((size_t)n_local * (size_t)p); dst = Xtmp.p; X_in = Xtmp.p; ld_in = n_local; }
+        ingest_f32(s, d->x, d->dtype, (size_t)n_local * (size_t)p, dst);
         ingest_f32(s, d->y, d->dtype, (size_t)n_local, ys.p);
     }
     T.ingest = tm.stop();
@@ -146,21 +155,24 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     DevBuf<float> d_meanX(p), d_scaleX(p);
     StdStats st;
     tm.start();
-    standardize_all(s, X_in, Xs.p, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
     T.standardize = tm.stop();
+    Xtmp.release();
 
     // ---- X'y, lambda0, Gram ------------------------------------------------------------------
     DevBuf<float> XY(ld);
     DevBuf<float> G((size_t)p * (size_t)ld);
     tm.start();
     XY.zero(s);
-    gemv_t<float>(s, Xs.p, n_local, p, n_local, ys.p, XY.p);
+    gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, XY.p);
     allreduce_sum(s, XY.p, p);
     G.zero(s);
-    const bool on_tensor = (ld == p) && gram_tn_tensor(s, Xs.p, n_local, p, G.p);
+    const char* gram_env = getenv("B200ADMM_GRAM");            // "simt" forces the CUDA-core kernel, "exact" the hi rewrite
+    const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
+    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, ldx, p, G.p, ld, (gram_env && !strcmp(gram_env, "exact")) ? 1 : 0);
     if (!on_tensor) {
         // CUDA-core path (shapes the tensor kernel does not take)
-        gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, n_local, Xs.p, n_local, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
+        gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
     }
     allreduce_sum(s, G.p, (size_t)p * (size_t)ld);
     std::vector<float> h_xy(p);

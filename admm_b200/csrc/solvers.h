@@ -52,7 +52,7 @@ void spd_inverse_f32(cudaStream_t s, float* a, i64 p, i64 ld, float* W, int* inf
 // stdize.cu pieces used by the drivers
 template <class T> void mean_from_sums(cudaStream_t s, const T* sums, i64 p, i64 n_total, T* mean);
 template <class T> void scale_from_sumsq(cudaStream_t s, const T* sumsq, i64 p, i64 n_total, bool sd_form, T* scale, T* inv);
-template <class T> void column_apply(cudaStream_t s, const T* Xin, T* Xout, i64 n, i64 p, i64 ld, const T* mean, const T* factor, const T* divisor);
+template <class T> void column_apply(cudaStream_t s, const T* Xin, T* Xout, i64 n, i64 p, i64 ld, i64 ld_out, const T* mean, const T* factor, const T* divisor);
 
 // solver_tall.cu / solver_wide.cu : admm_lasso / admm_enet (dispatch on n > p, Lasso.cpp:73-76)
 void solve_lasso_like(const LassoRequest& rq, b200admm_path* out);

@@ -64,13 +64,13 @@ __global__ void __launch_bounds__(STD_THREADS) col_sumsq_kernel(const T* __restr
 
 // out = (x - mean) * factor   or   (x - mean) / divisor;  null pointers skip the step
 template <class T>
-__global__ void __launch_bounds__(STD_THREADS) col_apply_kernel(const T* Xin, T* Xout, i64 n, i64 p, i64 ld,
+__global__ void __launch_bounds__(STD_THREADS) col_apply_kernel(const T* Xin, T* Xout, i64 n, i64 p, i64 ld, i64 ld_out,
                                                                 const T* __restrict__ mean, const T* __restrict__ factor,
                                                                 const T* __restrict__ divisor)
 {
     for (i64 j = blockIdx.x; j < p; j += gridDim.x) {
         const T* c = Xin + j * ld;
-        T* o = Xout + j * ld;
+        T* o = Xout + j * ld_out;
         const T mu = mean ? mean[j] : T(0);
         const T f = factor ? factor[j] : T(1);
         const T d = divisor ? divisor[j] : T(1);
@@ -133,7 +133,7 @@ template <class T> void column_center_sumsq(cudaStream_t s, T* X, i64 n, i64 p, 
 template <class T> void column_scale(cudaStream_t s, T* X, i64 n, i64 p, i64 ld, const T* inv_scale)
 {
     if (p <= 0) return;
-    col_apply_kernel<T><<<col_grid(p), STD_THREADS, 0, s>>>(X, X, n, p, ld, nullptr, inv_scale, nullptr);
+    col_apply_kernel<T><<<col_grid(p), STD_THREADS, 0, s>>>(X, X, n, p, ld, ld, nullptr, inv_scale, nullptr);
     KERNEL_CHECK();
 }
 
@@ -147,10 +147,10 @@ template <class T> void scale_from_sumsq(cudaStream_t s, const T* sumsq, i64 p, 
     scale_from_sumsq_kernel<T><<<(unsigned)((p + 255) / 256), 256, 0, s>>>(sumsq, p, n_total, sd_form ? 1 : 0, scale, inv);
     KERNEL_CHECK();
 }
-template <class T> void column_apply(cudaStream_t s, const T* Xin, T* Xout, i64 n, i64 p, i64 ld, const T* mean, const T* factor, const T* divisor)
+template <class T> void column_apply(cudaStream_t s, const T* Xin, T* Xout, i64 n, i64 p, i64 ld, i64 ld_out, const T* mean, const T* factor, const T* divisor)
 {
     if (p <= 0) return;
-    col_apply_kernel<T><<<col_grid(p), STD_THREADS, 0, s>>>(Xin, Xout, n, p, ld, mean, factor, divisor);
+    col_apply_kernel<T><<<col_grid(p), STD_THREADS, 0, s>>>(Xin, Xout, n, p, ld, ld_out, mean, factor, divisor);
     KERNEL_CHECK();
 }
 
@@ -166,22 +166,22 @@ void standardize_columns(cudaStream_t s, const T* X_in, T* X_out, i64 n, i64 p, 
         mean_from_sums(s, sums, p, n, sums);                       // mean, used only for the deviation
         col_sumsq_kernel<T><<<col_grid(p), STD_THREADS, 0, s>>>(X_in, nullptr, n, p, ld, sums, scaleX); KERNEL_CHECK();
         scale_from_sumsq(s, scaleX, p, n, true, scaleX, inv);
-        column_apply<T>(s, X_in, X_out, n, p, ld, nullptr, inv, nullptr);
+        column_apply<T>(s, X_in, X_out, n, p, ld, ld, nullptr, inv, nullptr);
         break;
     case 2:
         column_sums(s, X_in, n, p, ld, sums);
         mean_from_sums(s, sums, p, n, meanX);
-        column_apply<T>(s, X_in, X_out, n, p, ld, meanX, nullptr, nullptr);
+        column_apply<T>(s, X_in, X_out, n, p, ld, ld, meanX, nullptr, nullptr);
         break;
     case 3:
         column_sums(s, X_in, n, p, ld, sums);
         mean_from_sums(s, sums, p, n, meanX);
         col_sumsq_kernel<T><<<col_grid(p), STD_THREADS, 0, s>>>(X_in, nullptr, n, p, ld, meanX, scaleX); KERNEL_CHECK();
         scale_from_sumsq(s, scaleX, p, n, false, scaleX, inv);
-        column_apply<T>(s, X_in, X_out, n, p, ld, meanX, inv, nullptr);
+        column_apply<T>(s, X_in, X_out, n, p, ld, ld, meanX, inv, nullptr);
         break;
     default:
-        if (X_in != X_out) column_apply<T>(s, X_in, X_out, n, p, ld, nullptr, nullptr, nullptr);
+        if (X_in != X_out) column_apply<T>(s, X_in, X_out, n, p, ld, ld, nullptr, nullptr, nullptr);
         break;
     }
 }
@@ -197,7 +197,7 @@ template <class T> void standardize_y(cudaStream_t s, T* y, i64 n, int flag, T* 
         mean_from_sums(s, tmp, 1, n, tmp);
         col_sumsq_kernel<T><<<1, STD_THREADS, 0, s>>>(y, nullptr, n, 1, n, tmp, scaleY); KERNEL_CHECK();
         scale_from_sumsq<T>(s, scaleY, 1, n, true, scaleY, nullptr);
-        column_apply<T>(s, y, y, n, 1, n, nullptr, nullptr, scaleY);
+        column_apply<T>(s, y, y, n, 1, n, n, nullptr, nullptr, scaleY);
         break;
     case 2:
     case 3:
@@ -205,7 +205,7 @@ template <class T> void standardize_y(cudaStream_t s, T* y, i64 n, int flag, T* 
         mean_from_sums(s, tmp, 1, n, meanY);
         col_sumsq_kernel<T><<<1, STD_THREADS, 0, s>>>(y, nullptr, n, 1, n, meanY, scaleY); KERNEL_CHECK();
         scale_from_sumsq<T>(s, scaleY, 1, n, false, scaleY, nullptr);
-        column_apply<T>(s, y, y, n, 1, n, meanY, nullptr, scaleY);
+        column_apply<T>(s, y, y, n, 1, n, n, meanY, nullptr, scaleY);
         break;
     default:
         break;
@@ -226,7 +226,7 @@ void convert_f64_to_f32(cudaStream_t s, const double* in, float* out, size_t cou
     template void column_scale<T>(cudaStream_t, T*, i64, i64, i64, const T*);                                \
     template void mean_from_sums<T>(cudaStream_t, const T*, i64, i64, T*);                                   \
     template void scale_from_sumsq<T>(cudaStream_t, const T*, i64, i64, bool, T*, T*);                       \
-    template void column_apply<T>(cudaStream_t, const T*, T*, i64, i64, i64, const T*, const T*, const T*);  \
+    template void column_apply<T>(cudaStream_t, const T*, T*, i64, i64, i64, i64, const T*, const T*, const T*);  \
     template void standardize_columns<T>(cudaStream_t, const T*, T*, i64, i64, i64, int, T*, T*, T*);        \
     template void standardize_y<T>(cudaStream_t, T*, i64, int, T*, T*);
 INST(float)

@@ -179,3 +179,29 @@ def test_synth_design_statistics_and_sharding(K, torch):
     K.check(K.lib().b200admm_synth_f32(xs.data_ptr(), ys.data_ptr(), nr, p, r0, 123, 0.0, 2.0, 10, 1.0))
     assert np.array_equal(xs.cpu().numpy(), xa[:, r0:r0 + nr])
     assert np.array_equal(ys.cpu().numpy(), y.cpu().numpy()[r0:r0 + nr])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,p", [(4096, 256), (20000, 300), (1000, 8), (50000, 129), (16, 40), (2048 + 16, 512)])
+def test_gram_tensor_cores(K, torch, n, p, mode):
+    """tcgen05 3xTF32 Gram against float64: at least as accurate as the float32 CUDA-core kernel."""
+    rng = np.random.default_rng(n + p + mode)
+    x = (rng.normal(0.3, 2.0, size=(n, p))).astype(np.float32)
+    xd = colmajor_dev(torch, x)
+    g = torch.full((p, p), 7.0, device="cuda", dtype=torch.float32)     # the entry point zeroes it
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_gram_f32(xd.data_ptr(), n, p, g.data_ptr(), mode))
+    ref = x.astype(np.float64).T @ x.astype(np.float64)
+    got = g.cpu().numpy()
+    assert np.array_equal(got, got.T)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert (np.abs(got - ref) / scale).max() < 3e-6 * max(1.0, np.sqrt(n / 1000.0))
+
+
+def test_gram_tensor_rejects_unaligned(K, torch):
+    from admm_b200 import B200AdmmError
+    x = torch.zeros((64, 1001), device="cuda", dtype=torch.float32)     # n = 1001 is not a multiple of 4
+    g = torch.zeros((64, 64), device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    with pytest.raises(B200AdmmError):
+        K.check(K.lib().b200admm_k_gram_f32(x.data_ptr(), 1001, 64, g.data_ptr(), 1))
