@@ -1,0 +1,347 @@
+// admm_consensus.cu -- admm_parlasso: the reference's row-split (observation-split) global
+// consensus lasso, one block per GPU with ONE all-reduce per iteration.
+//
+// Reference being replaced (all in /root/reference/src):
+//   admm_parlasso()                         ParLasso.cpp:33-111
+//   PADMMBase_Master::solve / update_x / update_z / update_y / eps   PADMMBase.h:117-237
+//   PADMMBase_Worker::update_y                                        PADMMBase.h:65-74
+//   PADMMLasso_Worker::next_x / init / add_xu_to (incl. Woodbury)     PADMMLasso.h:17-68
+//   PADMMLasso_Master ctor (row split) / next_z / resid_dual / init   PADMMLasso.h:99-212
+//
+// Block i owns rows [i * floor(n/N), ...) (the last block also takes the remainder) and all p
+// columns; it keeps x_i, y_i and K_i^-1 = (A_i'A_i + rho I)^-1 (rho is fixed, so the reference's
+// per-iteration LLT solve becomes one bandwidth-bound product with the explicit inverse; blocks
+// with fewer rows than columns use the reference's Woodbury form with (A_i A_i' + rho I)^-1).
+//
+// Exchange step (the only one): the packed vector
+//     [ sum_i (x_i + y_i / rho)  (p floats) | sum_i |x_i|^2 | sum_i |x_i - z|^2 (previous iteration) | sum_i |y_i|^2 ]
+// is summed over ranks with one ncclAllReduce of p + 3 floats over NVLink.  The result is
+// bit-identical on every rank, so the z-update is computed redundantly everywhere and needs no
+// broadcast.  The primal residual of iteration t needs z(t), which only exists after the
+// exchange; it rides on the payload of iteration t + 1, i.e. the stopping rule is evaluated one
+// exchange late (the iterates, the returned z and the iteration count are exactly those of the
+// serial master loop; the price is one extra x-update per lambda).
+//
+// Without a communicator the N blocks live on one device and the same code runs with the
+// all-reduce degenerated to a no-op.  Compiled with --fmad=false.
+#include "solvers.h"
+#include "kernels.h"
+#include "comm.h"
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+#include <memory>
+
+namespace b200 {
+
+void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
+                       const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out);
+struct StdStats {
+    std::vector<float> meanX, scaleX;
+    float meanY = 0.f, scaleY = 1.f;
+};
+void standardize_all(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out, i64 ld_out, float* y, i64 n_local, i64 n_total, i64 p,
+                     int flag, float* d_meanX, float* d_scaleX, StdStats& st);
+
+namespace {
+
+constexpr int CT = 1024;
+
+// rhs = Ab - y + rho * z   (the rho * z term in double, only where z != 0: PADMMLasso.h:19-21)
+__global__ void __launch_bounds__(CT) cons_rhs_kernel(const float* __restrict__ Ab, const float* __restrict__ y, const float* __restrict__ z,
+                                                      double rho, int p, float* __restrict__ rhs)
+{
+    for (int j = blockIdx.x * CT + threadIdx.x; j < p; j += gridDim.x * CT) {
+        float v = Ab[j] - y[j];
+        const float zj = z[j];
+        if (zj != 0.f) v = (float)((double)v + rho * (double)zj);
+        rhs[j] = v;
+    }
+}
+// Woodbury tail: x = (rhs - t) / frho
+__global__ void __launch_bounds__(CT) cons_woodbury_kernel(const float* __restrict__ rhs, const float* __restrict__ t, float frho, int p, float* __restrict__ x)
+{
+    for (int j = blockIdx.x * CT + threadIdx.x; j < p; j += gridDim.x * CT) x[j] = (rhs[j] - t[j]) / frho;
+}
+// acc (+)= x + y / frho ; slot += |x|^2        (single CTA: deterministic)
+__global__ void __launch_bounds__(CT) cons_gather_kernel(const float* __restrict__ x, const float* __restrict__ y, float frho, int p,
+                                                         int first, float* __restrict__ acc, float* __restrict__ slot_x2)
+{
+    __shared__ float scratch[33];
+    float s = 0.f;
+    for (int j = threadIdx.x; j < p; j += CT) {
+        const float xv = x[j];
+        const float t = xv + y[j] / frho;
+        acc[j] = first ? t : acc[j] + t;
+        s += xv * xv;
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) *slot_x2 = first ? s : *slot_x2 + s;
+}
+// z_new = soft(acc / N, pen); out[0] = sum (z_new - z)^2, out[1] = |z_new|^2 ; z <- z_new
+__global__ void __launch_bounds__(CT) cons_z_kernel(const float* __restrict__ acc, float fN, double pen, int p, float* __restrict__ z, float* __restrict__ out2)
+{
+    __shared__ float scratch[33];
+    float d2 = 0.f, z2 = 0.f;
+    for (int j = threadIdx.x; j < p; j += CT) {
+        const float v = acc[j] / fN;
+        float zn;
+        if ((double)v > pen) zn = (float)((double)v - pen);
+        else if ((double)v < -pen) zn = (float)((double)v + pen);
+        else zn = 0.f;
+        const float dz = zn - z[j];
+        d2 += dz * dz; z2 += zn * zn;
+        z[j] = zn;
+    }
+    d2 = block_sum(d2, scratch);
+    z2 = block_sum(z2, scratch);
+    if (threadIdx.x == 0) { out2[0] = d2; out2[1] = z2; }
+}
+// r = x - z ; y += frho r ; slots: |r|^2, |y|^2
+__global__ void __launch_bounds__(CT) cons_dual_kernel(const float* __restrict__ x, const float* __restrict__ z, float frho, int p, int first,
+                                                       float* __restrict__ y, float* __restrict__ slot_r2, float* __restrict__ slot_y2)
+{
+    __shared__ float scratch[33];
+    float r2 = 0.f, y2 = 0.f;
+    for (int j = threadIdx.x; j < p; j += CT) {
+        const float r = x[j] - z[j];
+        const float yn = y[j] + frho * r;
+        y[j] = yn;
+        r2 += r * r; y2 += yn * yn;
+    }
+    r2 = block_sum(r2, scratch);
+    y2 = block_sum(y2, scratch);
+    if (threadIdx.x == 0) {
+        *slot_r2 = first ? r2 : *slot_r2 + r2;
+        *slot_y2 = first ? y2 : *slot_y2 + y2;
+    }
+}
+
+struct Block {
+    i64 rows = 0, row0 = 0;
+    bool tall = true;
+    DevBuf<float> Kinv;           // p x ld (tall) or rows x rows (Woodbury)
+    DevBuf<float> Ab, x, y;
+    DevBuf<float> t1, t2, work;   // Woodbury scratch
+};
+
+}  // namespace
+
+void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
+{
+    const b200admm_data* d = rq.d;
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    Comm& cm = comm();
+    if (d->dtype == B200ADMM_F64_DEVICE) throw ArgError("lasso computes in float32: pass f64 host, f32 host or f32 device data");
+    const i64 n_local = d->n, p = d->p;
+    const int N = nthread;
+    if (cm.active() && N != cm.nranks) throw ArgError("nthread must equal the number of ranks of the installed communicator");
+    const i64 n = cm.active() ? (i64)std::llround(allreduce_sum_host(s, (double)n_local)) : n_local;
+    if (p >= 2147483647LL / 4) throw ArgError("p too large");
+    const double t_begin = wall_now();
+    const int flag = (rq.standardize ? 1 : 0) + (rq.intercept ? 2 : 0);
+    const i64 ld = (p + 3) & ~(i64)3;
+    EventTimer tm(s);
+    b200admm_timing T;
+    memset(&T, 0, sizeof T);
+
+    // ---- ingest + global DataStd (ParLasso.cpp:45-69: standardisation happens before the split) ----
+    const i64 ldx = (n_local + 3) & ~(i64)3;
+    DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
+    const float* X_in = Xs.p;
+    i64 ld_in = ldx;
+    tm.start();
+    if (ldx != n_local) Xs.zero(s);
+    if (d->dtype == B200ADMM_F32_DEVICE) {
+        X_in = (const float*)d->x; ld_in = n_local;
+        CUDA_CHECK(cudaMemcpyAsync(ys.p, d->y, n_local * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+        float* dst = Xs.p;
+        if (ldx != n_local) { Xtmp.alloc((size_t)n_local * (size_t)p); dst = Xtmp.p; X_in = Xtmp.p; ld_in = n_local; }
+        ingest_f32(s, d->x, d->dtype, (size_t)n_local * (size_t)p, dst);
+        ingest_f32(s, d->y, d->dtype, (size_t)n_local, ys.p);
+    }
+    T.ingest = tm.stop();
+    DevBuf<float> d_meanX(p), d_scaleX(p);
+    StdStats st;
+    tm.start();
+    standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    T.standardize = tm.stop();
+    Xtmp.release();
+
+    // ---- row split (PADMMLasso.h:163-178) ---------------------------------------------------------
+    std::vector<std::unique_ptr<Block>> blocks;
+    if (cm.active()) {
+        // rank r must hold exactly the rows the reference gives worker r
+        const i64 chunk = n / N;
+        const i64 expect = cm.rank < N - 1 ? chunk : chunk + n % N;
+        if (n_local != expect) throw ArgError("row-sharded consensus: rank r must hold floor(n/N) rows (the last rank also the remainder)");
+        blocks.emplace_back(new Block());
+        blocks[0]->rows = n_local; blocks[0]->row0 = 0;
+    } else {
+        const i64 chunk = n / N;
+        if (chunk < 1) throw ArgError("more blocks than observations");
+        for (int i = 0; i < N; i++) {
+            blocks.emplace_back(new Block());
+            blocks[i]->row0 = i * chunk;
+            blocks[i]->rows = i < N - 1 ? chunk : chunk + n % N;
+        }
+    }
+
+    // ---- A_i'b_i, lambda0 = max |X'y| ---------------------------------------------------------------
+    DevBuf<float> xy(p);
+    tm.start();
+    for (size_t i = 0; i < blocks.size(); i++) {
+        Block& b = *blocks[i];
+        b.tall = b.rows >= p;
+        b.Ab.alloc(p); b.x.alloc(p); b.y.alloc(p);
+        gemv_t<float>(s, Xs.p + b.row0, b.rows, p, ldx, ys.p + b.row0, b.Ab.p);
+    }
+    gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, xy.p);       // X'y over all local rows, as the master does
+    allreduce_sum(s, xy.p, p);
+    std::vector<float> h_xy(p);
+    CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), xy.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    double lambda0 = 0;
+    for (i64 j = 0; j < p; j++) lambda0 = std::max(lambda0, (double)std::fabs(h_xy[j]));
+
+    std::vector<double> lam;
+    if (rq.nlambda_given < 1) {
+        if (rq.nlambda < 1) throw ArgError("nlambda must be at least 1");
+        const double lmax = lambda0 / (double)n * (double)st.scaleY;
+        make_lambda_grid(lmax, rq.lmin_ratio, rq.nlambda, lam);
+    } else {
+        if (!rq.lambda_given) throw ArgError("lambda is null");
+        lam.assign(rq.lambda_given, rq.lambda_given + rq.nlambda_given);
+    }
+    const int nl = (int)lam.size();
+    const double ilam0 = lam[0] * (double)n / (double)st.scaleY;
+    const double rho = rq.opts.rho > 0 ? rq.opts.rho : ilam0 / N;           // PADMMLasso.h:199-200
+    const float frho = (float)rho;
+
+    // ---- per block: Gram + rho I, explicit inverse (PADMMLasso_Worker::init) --------------------------
+    const char* gram_env = getenv("B200ADMM_GRAM");
+    const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
+    for (size_t i = 0; i < blocks.size(); i++) {
+        Block& b = *blocks[i];
+        const float* A = Xs.p + b.row0;
+        if (b.tall) {
+            b.Kinv.alloc((size_t)p * (size_t)ld);
+            b.Kinv.zero(s);
+            // (the tensor kernel declines block starts that are not 16-byte aligned; CUDA cores then)
+            const bool on_tensor = want_tensor && gram_tn_tensor(s, A, b.rows, ldx, p, b.Kinv.p, ld, 0);
+            if (!on_tensor)
+                gemm<float>(s, true, false, p, p, b.rows, 1.f, A, ldx, A, ldx, 0.f, b.Kinv.p, ld, GEMM_LOWER | GEMM_MIRROR);
+            add_to_diagonal(s, b.Kinv.p, ld, p, frho);
+            DevBuf<float> W((size_t)p * (size_t)ld);
+            int info = 0;
+            spd_inverse<float>(s, b.Kinv.p, p, ld, W.p, &info, nullptr);
+        } else {
+            const i64 m = b.rows;
+            b.Kinv.alloc((size_t)m * (size_t)m);
+            gemm<float>(s, false, true, m, m, p, 1.f, A, ldx, A, ldx, 0.f, b.Kinv.p, m, GEMM_LOWER | GEMM_MIRROR);
+            add_to_diagonal(s, b.Kinv.p, m, m, frho);
+            DevBuf<float> W((size_t)m * (size_t)m);
+            int info = 0;
+            spd_inverse<float>(s, b.Kinv.p, m, m, W.p, &info, nullptr);
+            b.t1.alloc(m); b.t2.alloc(std::max<i64>(m, p)); b.work.alloc(gemv_n_work(m, p));
+        }
+        b.x.zero(s); b.y.zero(s);
+    }
+    T.gram = tm.stop();          // Gram and factorisation are interleaved per block; reported together
+    bool keep_X = false;
+    for (auto& b : blocks) if (!b->tall) keep_X = true;
+    if (!keep_X) { Xs.release(); ys.release(); }
+
+    // ---- iterations ------------------------------------------------------------------------------------
+    DevBuf<float> z(p), rhs(p), payload(p + 3), zout2(2), local_tail(2);
+    z.zero(s);
+    CUDA_CHECK(cudaMemsetAsync(payload.p, 0, (p + 3) * sizeof(float), s));
+    CUDA_CHECK(cudaMemsetAsync(local_tail.p, 0, 2 * sizeof(float), s));
+    std::vector<float> z_all((size_t)nl * (size_t)p);
+    out->niter = (int*)malloc(sizeof(int) * nl);
+    out->lambda = (double*)malloc(sizeof(double) * nl);
+    if (!out->niter || !out->lambda) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
+    TraceRequest& tr = trace_request();
+    const double eps_abs = rq.opts.eps_abs, eps_rel = rq.opts.eps_rel;
+    const unsigned vg = (unsigned)std::max<i64>(1, std::min<i64>((p + CT - 1) / CT, 64));
+    const double sqrt_pN = std::sqrt((double)(p * N));
+    const int pi = (int)p;
+    // norms of the current iterate: global sum_i |x_i|^2, |z|^2 (sum_i |y_i|^2 arrives with each exchange)
+    double sx2 = 0, sz2 = 0;
+
+    tm.start();
+    for (int k = 0; k < nl; k++) {
+        const double lambda = lam[k] * (double)n / (double)st.scaleY;
+        const double pen = lambda / (rho * N);
+        const bool tracing = tr.buf && tr.cap > 0 && tr.which == k;
+        // Pass t performs the x-update of iteration t and one exchange, which also closes the books on
+        // iteration t - 1 (its primal residual needed z(t-1), i.e. the previous exchange).
+        double eps_p_cur = 0, eps_d_cur = 0, rd_cur = 0;
+        bool have_prev = false;
+        int niter = rq.opts.maxit + 1;
+        for (int t = 0; t <= rq.opts.maxit; t++) {
+            for (size_t i = 0; i < blocks.size(); i++) {
+                Block& b = *blocks[i];
+                cons_rhs_kernel<<<vg, CT, 0, s>>>(b.Ab.p, b.y.p, z.p, rho, pi, rhs.p); KERNEL_CHECK();
+                if (b.tall) {
+                    gemv_t<float>(s, b.Kinv.p, p, p, ld, rhs.p, b.x.p);                        // K_i^-1 rhs (symmetric)
+                } else {
+                    const float* A = Xs.p + b.row0;
+                    gemv_n<float>(s, A, b.rows, p, ldx, rhs.p, b.t1.p, b.work.p);              // A rhs
+                    gemv_t<float>(s, b.Kinv.p, b.rows, b.rows, b.rows, b.t1.p, b.t2.p);        // (AA' + rho I)^-1 (.)
+                    gemv_t<float>(s, A, b.rows, p, ldx, b.t2.p, b.x.p);                        // A'(.)
+                    cons_woodbury_kernel<<<vg, CT, 0, s>>>(rhs.p, b.x.p, frho, pi, b.x.p); KERNEL_CHECK();
+                }
+                cons_gather_kernel<<<1, CT, 0, s>>>(b.x.p, b.y.p, frho, pi, i == 0 ? 1 : 0, payload.p, payload.p + p); KERNEL_CHECK();
+            }
+            // local sum_i |x_i - z|^2 and sum_i |y_i|^2 left by the previous dual update ride along
+            CUDA_CHECK(cudaMemcpyAsync(payload.p + p + 1, local_tail.p, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            allreduce_sum(s, payload.p, (size_t)p + 3);                                         // THE exchange
+            float tail[3];
+            CUDA_CHECK(cudaMemcpyAsync(tail, payload.p + p, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            if (have_prev) {
+                const double rp_prev = std::sqrt((double)tail[1]);
+                if (tracing && t - 1 < tr.cap) {
+                    double* row = tr.buf + 5 * (size_t)(t - 1);
+                    row[0] = eps_p_cur; row[1] = rp_prev; row[2] = eps_d_cur; row[3] = rd_cur; row[4] = rho;
+                    if (tr.nrows) *tr.nrows = t;
+                }
+                if (rp_prev < eps_p_cur && rd_cur < eps_d_cur) { niter = t; break; }   // iteration t-1 converged: returns (t-1)+1
+            }
+            if (t == rq.opts.maxit) break;                                             // only closing the books
+            // tolerances of iteration t, from the iterate before it (PADMMBase.h:117-138)
+            eps_p_cur = std::max(std::sqrt(sx2), std::sqrt(sz2) * std::sqrt((double)N)) * eps_rel + sqrt_pN * eps_abs;
+            eps_d_cur = std::sqrt((double)tail[2]) * eps_rel + sqrt_pN * eps_abs;
+            // z-update (identical on every rank), then the dual update of the local blocks
+            cons_z_kernel<<<1, CT, 0, s>>>(payload.p, (float)N, pen, pi, z.p, zout2.p); KERNEL_CHECK();
+            for (size_t i = 0; i < blocks.size(); i++) {
+                Block& b = *blocks[i];
+                cons_dual_kernel<<<1, CT, 0, s>>>(b.x.p, z.p, frho, pi, i == 0 ? 1 : 0, b.y.p, local_tail.p, local_tail.p + 1); KERNEL_CHECK();
+            }
+            float z2[2];
+            CUDA_CHECK(cudaMemcpyAsync(z2, zout2.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            rd_cur = rho * std::sqrt((double)N * (double)z2[0]);                        // PADMMLasso.h:151-154
+            sz2 = (double)z2[1];
+            sx2 = (double)tail[0];
+            have_prev = true;
+        }
+        out->niter[k] = niter;
+        out->lambda[k] = lam[k];
+        CUDA_CHECK(cudaMemcpyAsync(z_all.data() + (size_t)k * p, z.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    T.iterate = tm.stop();
+
+    tm.start();
+    out->nlambda = nl;
+    finish_lasso_path(z_all, nl, p, flag, st.meanX, st.scaleX, st.meanY, st.scaleY, out);
+    T.finish = tm.stop();
+    T.total = wall_now() - t_begin;
+    out->rho = rho; out->eig = 0; out->lambda0 = lambda0; out->t = T;
+}
+
+}  // namespace b200

@@ -1,0 +1,451 @@
+// admm_wide.cu -- lasso / elastic net for n <= p: the reference's linearised ADMM with
+// active-set updates (float32 vectors, double scalars).
+//
+// Reference being replaced (all in /root/reference/src):
+//   ADMMBase::solve / update_x / update_z / update_y / update_rho   ADMMBase.h:73-109,158-216
+//   ADMMLassoWide ctor / init / init_warm                           ADMMLassoWide.h:189-251
+//   ADMMLassoWide::next_x / active_set_update / is_regular_update   ADMMLassoWide.h:86-155
+//   ADMMLassoWide::next_z / next_residual / compute_eps_* / resid   ADMMLassoWide.h:156-186
+//   ADMMEnetWide::next_x / active_set_update / enet                 ADMMEnet.h:62-154
+//   the wide branch of admm_lasso() / admm_enet()                   Lasso.cpp:75-76,112-123
+//
+// x (length p) is kept dense together with its sorted support list; the three data passes of
+// an iteration are HBM streams over columns of X (column-major, so a column is contiguous):
+//   regular step  (iterations 4^k - 1):  vec = X' tmp over ALL p columns (gemv_t), prox, support rebuild
+//   active step   (all others)        :  one warp per support column: x_j - X_j' tmp, prox, prune
+//   z step                            :  Ax = sum over support columns (row-parallel, fixed chunk order),
+//                                        fused with z = (y_dat + u + rho Ax)/(-1-rho), r = Ax + z, u += rho r
+//                                        and the five squared norms the stopping rule needs.
+// The loop is driven from the host (the support size is data dependent): one small
+// device->host read per iteration.  Compiled with --fmad=false (unfused, reference order).
+#include "solvers.h"
+#include "kernels.h"
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+
+namespace b200 {
+
+void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
+                       const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out);
+
+namespace {
+
+constexpr int WT = 256;
+
+struct WideProx {
+    int enet;
+    double pen_d;      // lambda / (rho * gamma) in double (regular step, lasso)
+    float pen_f;       // the same rounded to float (active step; enet parameters)
+    float thresh, denom;
+};
+
+__device__ __forceinline__ float prox_regular(float v, const WideProx& q)
+{
+    if (!q.enet) {
+        if ((double)v > q.pen_d) return (float)((double)v - q.pen_d);
+        if ((double)v < -q.pen_d) return (float)((double)v + q.pen_d);
+        return 0.f;
+    }
+    if (v > q.thresh) return (v - q.thresh) / q.denom;
+    if (v < -q.thresh) return (v + q.thresh) / q.denom;
+    return 0.f;
+}
+__device__ __forceinline__ float prox_active(float v, const WideProx& q)
+{
+    if (!q.enet) {
+        if (v > q.pen_f) return v - q.pen_f;
+        if (v < -q.pen_f) return v + q.pen_f;
+        return 0.f;
+    }
+    if (v > q.thresh) return (v - q.thresh) / q.denom;
+    if (v < -q.thresh) return (v + q.thresh) / q.denom;
+    return 0.f;
+}
+
+// tmp = (Ax + z) + y / frho      [optionally / gamma]
+__global__ void __launch_bounds__(WT) wide_tmp_kernel(const float* __restrict__ Ax, const float* __restrict__ z, const float* __restrict__ y,
+                                                      float frho, float gamma, int divide, i64 n, float* __restrict__ tmp)
+{
+    const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
+    if (i >= n) return;
+    float t = (Ax[i] + z[i]) + y[i] / frho;
+    if (divide) t = t / gamma;
+    tmp[i] = t;
+}
+
+// regular step, second half: x_j = prox(-vec_j / gamma + x_j) for every j
+__global__ void __launch_bounds__(WT) wide_prox_all_kernel(const float* __restrict__ vec, float* __restrict__ x, i64 p, float gamma, WideProx q)
+{
+    const i64 j = (i64)blockIdx.x * WT + threadIdx.x;
+    if (j >= p) return;
+    const float v = -vec[j] / gamma + x[j];
+    x[j] = prox_regular(v, q);
+}
+
+// active step: one warp per support column
+__global__ void __launch_bounds__(WT) wide_active_kernel(const float* __restrict__ X, i64 ldx, i64 n, const float* __restrict__ tmp,
+                                                         const int* __restrict__ supp, int nnz, float* __restrict__ x, WideProx q)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * WT) >> 5;
+    for (int k = (blockIdx.x * WT + threadIdx.x) >> 5; k < nnz; k += warps) {
+        const int j = supp[k];
+        const float* col = X + (i64)j * ldx;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        i64 i = lane;
+        for (; i + 96 < n; i += 128) {
+            s0 = fmaf(tmp[i], col[i], s0); s1 = fmaf(tmp[i + 32], col[i + 32], s1);
+            s2 = fmaf(tmp[i + 64], col[i + 64], s2); s3 = fmaf(tmp[i + 96], col[i + 96], s3);
+        }
+        for (; i < n; i += 32) s0 = fmaf(tmp[i], col[i], s0);
+        const float d = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) x[j] = prox_active(x[j] - d, q);
+    }
+}
+
+// ---- stable compaction of "x[j] != 0" into a sorted index list ---------------------------------
+// src == nullptr: candidates are 0..len-1; otherwise candidates are src[0..len-1] (already sorted)
+__global__ void __launch_bounds__(1024) compact_count_kernel(const int* __restrict__ src, const float* __restrict__ x, int len, int* __restrict__ counts)
+{
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    int keep = 0;
+    if (i < len) { const int j = src ? src[i] : i; keep = x[j] != 0.f; }
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) counts[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ counts, int nb, int* __restrict__ total)
+{
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? counts[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nb) counts[i] = carry + sh[threadIdx.x] - v;      // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(1024) compact_scatter_kernel(const int* __restrict__ src, const float* __restrict__ x, int len,
+                                                               const int* __restrict__ offsets, int* __restrict__ out)
+{
+    __shared__ int wsum[32];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    int keep = 0, j = 0;
+    if (i < len) { j = src ? src[i] : i; keep = x[j] != 0.f; }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wsum[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane];
+        for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += t; }
+        wsum[lane] = v - wsum[lane];                                 // exclusive warp offsets
+    }
+    __syncthreads();
+    if (keep) out[offsets[blockIdx.x] + wsum[warp] + __popc(ballot & ((1u << lane) - 1u))] = j;
+}
+
+// ---- z step ----------------------------------------------------------------------------------------
+// partial Ax over a chunk of the support: part[chunk][i] = sum_k X(i, supp_k) * x[supp_k]
+__global__ void __launch_bounds__(WT) wide_ax_kernel(const float* __restrict__ X, i64 ldx, i64 n, const int* __restrict__ supp, int nnz,
+                                                     const float* __restrict__ x, int per_chunk, float* __restrict__ part)
+{
+    __shared__ int sj[WT];
+    __shared__ float sv[WT];
+    const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
+    const int k0 = blockIdx.y * per_chunk, k1 = min(nnz, k0 + per_chunk);
+    float acc = 0.f;
+    for (int kb = k0; kb < k1; kb += WT) {
+        const int cnt = min(WT, k1 - kb);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) { const int j = supp[kb + threadIdx.x]; sj[threadIdx.x] = j; sv[threadIdx.x] = x[j]; }
+        __syncthreads();
+        if (i < n) {
+            int k = 0;
+            for (; k + 4 <= cnt; k += 4) {
+                const float a0 = X[i + (i64)sj[k] * ldx], a1 = X[i + (i64)sj[k + 1] * ldx];
+                const float a2 = X[i + (i64)sj[k + 2] * ldx], a3 = X[i + (i64)sj[k + 3] * ldx];
+                acc += a0 * sv[k]; acc += a1 * sv[k + 1]; acc += a2 * sv[k + 2]; acc += a3 * sv[k + 3];
+            }
+            for (; k < cnt; k++) acc += X[i + (i64)sj[k] * ldx] * sv[k];
+        }
+    }
+    if (i < n) part[(i64)blockIdx.y * n + i] = acc;
+}
+
+// Ax = sum of chunks (fixed order); z = (ydat + y + frho Ax) / den; r = Ax + z; y += frho r; norms
+__global__ void __launch_bounds__(WT) wide_zstep_kernel(const float* __restrict__ part, int chunks, i64 n, const float* __restrict__ ydat,
+                                                        float frho, float den, float* __restrict__ Ax, float* __restrict__ z,
+                                                        float* __restrict__ y, float* __restrict__ psums)
+{
+    const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
+    float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (i < n) {
+        float ax = 0.f;
+        for (int c = 0; c < chunks; c++) ax += part[(i64)c * n + i];
+        const float yo = y[i];
+        const float zn = ((ydat[i] + yo) + frho * ax) / den;
+        const float dz = zn - z[i];
+        const float r = ax + zn;
+        const float yn = yo + frho * r;
+        Ax[i] = ax; z[i] = zn; y[i] = yn;
+        ps[0] = dz * dz; ps[1] = r * r; ps[2] = ax * ax; ps[3] = zn * zn; ps[4] = yn * yn;
+    }
+    __shared__ float s_red[WT / 32][5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 5; q++) ps[q] = warp_sum(ps[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) s_red[warp][q] = ps[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float s = 0.f;
+        for (int w = 0; w < WT / 32; w++) s += s_red[w][threadIdx.x];
+        psums[(size_t)blockIdx.x * 5 + threadIdx.x] = s;
+    }
+}
+__global__ void wide_finish_sums_kernel(const float* __restrict__ psums, int nblocks, const int* __restrict__ nnz, double* __restrict__ out6)
+{
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q < 5) {
+        double s = 0.0;
+        for (int b = lane; b < nblocks; b += 32) s += (double)psums[(size_t)b * 5 + q];
+        s = warp_sum(s);
+        if (lane == 0) out6[q] = s;
+    } else if (q == 5 && lane == 0) out6[5] = (double)*nnz;
+}
+
+inline bool is_regular_update(unsigned c)
+{
+    if (c == 0 || c == 3 || c == 15 || c == 63) return true;
+    c++;
+    if (c & (c - 1)) return false;
+    return (c & 0x55555555u) != 0;
+}
+inline void balance_rho(double& rho, double rp, double ep, double rd, double ed)
+{
+    if (rp / ep > 10 * rd / ed) rho *= 2;
+    else if (rd / ed > 10 * rp / ep) rho /= 2;
+    if (rp < ep) rho /= 1.2;
+    if (rd < ed) rho *= 1.2;
+}
+
+// C (n x n, full) = X X' accumulated over column chunks so that no float sum runs over more than
+// 8192 terms before it is folded into C (keeps the float32 result unbiased for p ~ 1e6)
+void gram_nt_chunked(cudaStream_t s, const float* X, i64 n, i64 p, i64 ldx, float* C)
+{
+    const i64 chunk = 8192;
+    for (i64 k0 = 0; k0 < p; k0 += chunk) {
+        const i64 kc = std::min(chunk, p - k0);
+        const bool last = k0 + kc >= p;
+        gemm<float>(s, false, true, n, n, kc, 1.f, X + k0 * ldx, ldx, X + k0 * ldx, ldx, k0 == 0 ? 0.f : 1.f, C, n,
+                    GEMM_LOWER | (last ? GEMM_MIRROR : 0));
+    }
+}
+
+}  // namespace
+
+void solve_wide(const LassoRequest& rq, b200admm_path* out)
+{
+    const b200admm_data* d = rq.d;
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const i64 n = d->n, p = d->p;
+    if (d->dtype == B200ADMM_F64_DEVICE) throw ArgError("lasso / enet compute in float32: pass f64 host, f32 host or f32 device data");
+    if (n < 3) throw CodeError(B200ADMM_ELANCZOS, "coarse eigenvalue estimate needs at least 3 observations (Spectra: 1 <= nev < ncv <= n)");
+    const double t_begin = wall_now();
+    const int flag = (rq.standardize ? 1 : 0) + (rq.intercept ? 2 : 0);
+    EventTimer tm(s);
+    b200admm_timing T;
+    memset(&T, 0, sizeof T);
+
+    // ---- ingest + DataStd (Lasso.cpp:45-68) -----------------------------------------------------
+    DevBuf<float> Xs((size_t)n * (size_t)p), ydat(n);
+    const float* X_in = Xs.p;
+    tm.start();
+    if (d->dtype == B200ADMM_F32_DEVICE) {
+        X_in = (const float*)d->x;
+        CUDA_CHECK(cudaMemcpyAsync(ydat.p, d->y, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+        ingest_f32(s, d->x, d->dtype, (size_t)n * (size_t)p, Xs.p);
+        ingest_f32(s, d->y, d->dtype, (size_t)n, ydat.p);
+    }
+    T.ingest = tm.stop();
+    DevBuf<float> d_meanX(p), d_scaleX(p), tmpv(2 * p + 8), y2(2);
+    tm.start();
+    d_meanX.zero(s);
+    CUDA_CHECK(cudaMemsetAsync(y2.p, 0, 2 * sizeof(float), s));
+    standardize_y<float>(s, ydat.p, n, flag, y2.p, tmpv.p);
+    standardize_columns<float>(s, X_in, Xs.p, n, p, n, flag, d_meanX.p, d_scaleX.p, tmpv.p);
+    std::vector<float> meanX(p, 0.f), scaleX(p, 1.f);
+    float h2[2] = {0.f, 1.f};
+    if (flag >= 2) CUDA_CHECK(cudaMemcpyAsync(meanX.data(), d_meanX.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (flag & 1) CUDA_CHECK(cudaMemcpyAsync(scaleX.data(), d_scaleX.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (flag) CUDA_CHECK(cudaMemcpyAsync(h2, y2.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    T.standardize = tm.stop();
+    const float meanY = flag >= 2 ? h2[0] : 0.f, scaleY = flag ? h2[1] : 1.f;
+    const float* X = Xs.p;
+    const i64 ldx = n;
+
+    // ---- ctor: lambda0 = max |X'y|, gamma = coarse lambda_max(XX') (ADMMLassoWide.h:189-212) ------
+    DevBuf<float> vec(p);
+    tm.start();
+    gemv_t<float>(s, X, n, p, ldx, ydat.p, vec.p);
+    std::vector<float> h_xy(p);
+    CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), vec.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    float sprad = 0.f;
+    {
+        DevBuf<float> Gn((size_t)n * (size_t)n);
+        gram_nt_chunked(s, X, n, p, ldx, Gn.p);
+        T.gram = tm.stop();
+        tm.start();
+        sprad = coarse_eig_device(s, Gn.p, n, n, nullptr);
+        T.eig = tm.stop();
+    }
+    float lambda0 = 0.f;
+    for (i64 j = 0; j < p; j++) lambda0 = std::max(lambda0, std::fabs(h_xy[j]));
+    const float alpha_f = (float)rq.alpha;
+    if (rq.enet) lambda0 = (float)((double)lambda0 / ((double)alpha_f + 0.0001));
+
+    // ---- lambda sequence ---------------------------------------------------------------------------
+    std::vector<double> lam;
+    if (rq.nlambda_given < 1) {
+        if (rq.nlambda < 1) throw ArgError("nlambda must be at least 1");
+        const double lmax = (double)lambda0 / (double)n * (double)scaleY;
+        make_lambda_grid(lmax, rq.lmin_ratio, rq.nlambda, lam);
+    } else {
+        if (!rq.lambda_given) throw ArgError("lambda is null");
+        lam.assign(rq.lambda_given, rq.lambda_given + rq.nlambda_given);
+    }
+    const int nl = (int)lam.size();
+
+    // ---- state ---------------------------------------------------------------------------------------
+    DevBuf<float> x(p), Ax(n), z(n), y(n), tmp(n);
+    DevBuf<int> supp[2], nnz_dev(1), counts((size_t)((p + 1023) / 1024 + 1));
+    supp[0].alloc(p); supp[1].alloc(p);
+    x.zero(s); Ax.zero(s); z.zero(s); y.zero(s); nnz_dev.zero(s);
+    const int zblocks = (int)((n + WT - 1) / WT);
+    DevBuf<float> psums((size_t)zblocks * 5);
+    DevBuf<double> sums6(6);
+    int max_chunks = 64;
+    DevBuf<float> part((size_t)max_chunks * (size_t)n);
+    int cur_supp = 0, nnz = 0;
+
+    auto compact = [&](const int* src, int len, int* dst) {
+        const int nb = (len + 1023) / 1024;
+        if (nb == 0) { CUDA_CHECK(cudaMemsetAsync(nnz_dev.p, 0, sizeof(int), s)); return; }
+        compact_count_kernel<<<nb, 1024, 0, s>>>(src, x.p, len, counts.p); KERNEL_CHECK();
+        compact_scan_kernel<<<1, 1024, 0, s>>>(counts.p, nb, nnz_dev.p); KERNEL_CHECK();
+        compact_scatter_kernel<<<nb, 1024, 0, s>>>(src, x.p, len, counts.p, dst); KERNEL_CHECK();
+    };
+
+    TraceRequest& tr = trace_request();
+    std::vector<float> x_all((size_t)nl * (size_t)p);
+    out->niter = (int*)malloc(sizeof(int) * nl);
+    out->lambda = (double*)malloc(sizeof(double) * nl);
+    if (!out->niter || !out->lambda) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
+
+    double rho = rq.opts.rho;
+    double sAx2 = 0, sz2 = 0, sy2 = 0;                      // squared norms of the current Ax, z, y
+    const double eps_abs = rq.opts.eps_abs, eps_rel = rq.opts.eps_rel;
+    const float gamma = sprad;
+    const float sqrt_sprad = std::sqrt(sprad);
+    tm.start();
+    for (int k = 0; k < nl; k++) {
+        const float lambda = (float)(lam[k] * (double)n / (double)scaleY);      // Lasso.cpp:99, stored as Scalar
+        if (k == 0) {
+            if (rho <= 0) rho = std::pow((double)(lambda / sprad), 1.0 / 3);    // ADMMLassoWide.h:228-229
+        }
+        unsigned iter_counter = 0;                                                // init / init_warm
+        const bool tracing = tr.buf && tr.cap > 0 && tr.which == k;
+        int i;
+        for (i = 0; i < rq.opts.maxit; i++) {
+            const double eps_primal = std::max((double)std::sqrt((float)sAx2), (double)std::sqrt((float)sz2)) * eps_rel + std::sqrt((double)n) * eps_abs;
+            const double eps_dual = (double)(sqrt_sprad * std::sqrt((float)sy2)) * eps_rel + std::sqrt((double)p) * eps_abs;
+            const float frho = (float)rho;
+            // ---------------- x step ----------------
+            if (!rq.enet && (double)lambda > (double)lambda0 - 1e-5) {
+                if (nnz > 0) { x.zero(s); nnz = 0; CUDA_CHECK(cudaMemsetAsync(nnz_dev.p, 0, sizeof(int), s)); }
+            } else {
+                WideProx q;
+                q.enet = rq.enet ? 1 : 0;
+                q.pen_d = (double)lambda / (rho * (double)gamma);
+                q.pen_f = (float)q.pen_d;
+                const bool regular = is_regular_update(iter_counter) && (!rq.enet || lambda < lambda0);
+                if (regular) {
+                    q.thresh = (float)((double)alpha_f * q.pen_d);                 // enet(): Scalar thresh = alpha * penalty(double)
+                    q.denom = (float)(1.0 + q.pen_d * (1.0 - (double)alpha_f));
+                    wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, frho, gamma, 0, n, tmp.p); KERNEL_CHECK();
+                    gemv_t<float>(s, X, n, p, ldx, tmp.p, vec.p);
+                    wide_prox_all_kernel<<<(unsigned)((p + WT - 1) / WT), WT, 0, s>>>(vec.p, x.p, p, gamma, q); KERNEL_CHECK();
+                    compact(nullptr, (int)p, supp[cur_supp].p);
+                } else {
+                    q.thresh = alpha_f * q.pen_f;                                  // active_set_update(): all Scalar
+                    q.denom = (float)(1.0 + (double)q.pen_f * (1.0 - (double)alpha_f));
+                    if (nnz > 0) {
+                        wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, frho, gamma, 1, n, tmp.p); KERNEL_CHECK();
+                        const int blocks = std::min((nnz + 7) / 8, sm_count() * 8);
+                        wide_active_kernel<<<blocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cur_supp].p, nnz, x.p, q); KERNEL_CHECK();
+                        compact(supp[cur_supp].p, nnz, supp[cur_supp ^ 1].p);
+                        cur_supp ^= 1;
+                    }
+                }
+                iter_counter++;
+                CUDA_CHECK(cudaMemcpyAsync(&nnz, nnz_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                CUDA_CHECK(cudaStreamSynchronize(s));
+            }
+            // ---------------- z step, residual, dual update ----------------
+            int chunks = std::max(1, std::min(max_chunks, (nnz + 255) / 256));
+            const int per_chunk = nnz > 0 ? (nnz + chunks - 1) / chunks : 0;
+            if (nnz == 0) chunks = 0;
+            if (chunks > 0) {
+                wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks), WT, 0, s>>>(X, ldx, n, supp[cur_supp].p, nnz, x.p, per_chunk, part.p);
+                KERNEL_CHECK();
+            }
+            wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, chunks, n, ydat.p, frho, (float)(-1 - rho), Ax.p, z.p, y.p, psums.p); KERNEL_CHECK();
+            wide_finish_sums_kernel<<<1, 192, 0, s>>>(psums.p, zblocks, nnz_dev.p, sums6.p); KERNEL_CHECK();
+            double h[6];
+            CUDA_CHECK(cudaMemcpyAsync(h, sums6.p, sizeof h, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            const double resid_dual = rho * (double)sqrt_sprad * (double)std::sqrt((float)h[0]);
+            const double resid_primal = (double)std::sqrt((float)h[1]);
+            sAx2 = h[2]; sz2 = h[3]; sy2 = h[4];
+            if (tracing && i < tr.cap) {
+                double* row = tr.buf + 5 * (size_t)i;
+                row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
+                if (tr.nrows) *tr.nrows = i + 1;
+            }
+            if (resid_primal < eps_primal && resid_dual < eps_dual) break;
+            if (i > 3) balance_rho(rho, resid_primal, eps_primal, resid_dual, eps_dual);
+        }
+        out->niter[k] = i + 1;
+        out->lambda[k] = lam[k];
+        CUDA_CHECK(cudaMemcpyAsync(x_all.data() + (size_t)k * p, x.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    T.iterate = tm.stop();
+
+    tm.start();
+    out->nlambda = nl;
+    finish_lasso_path(x_all, nl, p, flag, meanX, scaleX, meanY, scaleY, out);
+    T.finish = tm.stop();
+    T.total = wall_now() - t_begin;
+    out->rho = rho; out->eig = sprad; out->lambda0 = lambda0; out->t = T;
+}
+
+}  // namespace b200

@@ -236,20 +236,30 @@ float coarse_eig_device(cudaStream_t s, const float* S, i64 n, i64 lds, int* nma
     return ev;
 }
 
-// a <- a^-1 for the SPD matrix in `a` (p x p, ld), full symmetric result.  W: p x ld scratch.
-void spd_inverse_f32(cudaStream_t s, float* a, i64 p, i64 ld, float* W, int* info_host)
+// a <- a^-1 for the SPD matrix in `a` (p x p, ld), full symmetric result.  W: p x ld scratch,
+// left holding L^-1 (lower triangular).  keep_factor: copy of the Cholesky factor L (p x ld) or null.
+template <class T>
+void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* keep_factor)
 {
-    DevBuf<float> work(chol_work<float>(p));
-    DevBuf<float> tmp((size_t)p * 128);
+    DevBuf<T> work(chol_work<T>(p));
+    DevBuf<T> tmp((size_t)p * 128);
     DevBuf<int> info(1);
-    chol_lower<float>(s, a, p, ld, work.p, info.p);
+    chol_lower<T>(s, a, p, ld, work.p, info.p);
     int h = 0;
     CUDA_CHECK(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     if (info_host) *info_host = h;
     if (h != 0) throw CodeError(B200ADMM_ENOTSPD, "Cholesky factorisation met a non-positive pivot at column " + std::to_string(h));
-    tri_inverse_lower<float>(s, a, p, ld, work.p, W, ld, tmp.p);
-    gram_of_lower<float>(s, W, p, ld, a, ld);
+    if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
+    tri_inverse_lower<T>(s, a, p, ld, work.p, W, ld, tmp.p);
+    gram_of_lower<T>(s, W, p, ld, a, ld);
+}
+template void spd_inverse<float>(cudaStream_t, float*, i64, i64, float*, int*, float*);
+template void spd_inverse<double>(cudaStream_t, double*, i64, i64, double*, int*, double*);
+
+void spd_inverse_f32(cudaStream_t s, float* a, i64 p, i64 ld, float* W, int* info_host)
+{
+    spd_inverse<float>(s, a, p, ld, W, info_host, nullptr);
 }
 
 }  // namespace b200
@@ -462,8 +472,8 @@ int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g, int use_te
         bool done = false;
         if (use_tensor) {
             CUDA_CHECK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)p * (size_t)p, c.stream));
-            done = gram_tn_tensor(c.stream, (const float*)x, n, p, (float*)g, p, use_tensor > 1 ? 1 : 0);
-            if (!done) throw ArgError("tensor-core Gram kernel cannot take this shape (needs n % 4 == 0, n >= 16, p >= 8)");
+            done = gram_tn_tensor(c.stream, (const float*)x, n, n, p, (float*)g, p, use_tensor > 1 ? 1 : 0);
+            if (!done) throw ArgError("tensor-core Gram kernel cannot take this shape (needs n % 4 == 0 and p >= 8)");
         }
         if (!done)
             gemm<float>(c.stream, true, false, p, p, n, 1.f, (const float*)x, n, (const float*)x, n, 0.f, (float*)g, p, GEMM_LOWER | GEMM_MIRROR);

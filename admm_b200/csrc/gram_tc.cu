@@ -244,21 +244,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int ks = 0; ks < nk; ks++) {
                 mbar_wait(smem_u32(full_raw + r.idx), r.phase);
                 mbar_wait(smem_u32(empty_lo + q.idx), q.phase ^ 1u);
-                uint4* src = reinterpret_cast<uint4*>(raw + r.idx * STAGE_BYTES);
-                float4* dst = reinterpret_cast<float4*>(lo + q.idx * STAGE_BYTES);
+                const uint32_t src = smem_u32(raw + r.idx * STAGE_BYTES) + (uint32_t)st * 16u;
+                const uint32_t dst = smem_u32(lo + q.idx * STAGE_BYTES) + (uint32_t)st * 16u;
 #pragma unroll 4
                 for (int i = 0; i < STAGE_BYTES / 16 / SPLIT_THREADS; i++) {
-                    const int e = st + i * SPLIT_THREADS;
-                    const uint4 v = src[e];
+                    const uint32_t off = (uint32_t)i * (SPLIT_THREADS * 16u);
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
                     uint4 h;
                     h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                    float4 l;
-                    l.x = __uint_as_float(v.x) - __uint_as_float(h.x);
-                    l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
-                    l.z = __uint_as_float(v.z) - __uint_as_float(h.z);
-                    l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
-                    dst[e] = l;
-                    if (exact_hi) src[e] = h;
+                    const float lx = __uint_as_float(v.x) - __uint_as_float(h.x);
+                    const float ly = __uint_as_float(v.y) - __uint_as_float(h.y);
+                    const float lz = __uint_as_float(v.z) - __uint_as_float(h.z);
+                    const float lw = __uint_as_float(v.w) - __uint_as_float(h.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(dst + off), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+                    if (exact_hi)
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(src + off), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
                 }
                 fence_proxy_async();
                 mbar_arrive(smem_u32(full_lo + q.idx));
@@ -349,10 +350,10 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
-void make_map(CUtensorMap* m, const float* X, i64 n, i64 p, int box_cols)
+void make_map(CUtensorMap* m, const float* X, i64 n, i64 ldx, i64 p, int box_cols)
 {
     cuuint64_t gdim[2] = { (cuuint64_t)n, (cuuint64_t)p };
-    cuuint64_t gstride[1] = { (cuuint64_t)n * sizeof(float) };
+    cuuint64_t gstride[1] = { (cuuint64_t)ldx * sizeof(float) };
     cuuint32_t box[2] = { (cuuint32_t)BK, (cuuint32_t)box_cols };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estr,
@@ -364,13 +365,14 @@ void make_map(CUtensorMap* m, const float* X, i64 n, i64 p, int box_cols)
 }  // namespace
 
 // Writes the full symmetric p x p matrix into G (leading dimension ld).
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 p, float* G, i64 ld, int exact_hi)
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi)
 {
-    if (n % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < BK || p < 8) return false;
+    // TMA: 16-byte aligned base and column stride; rows beyond n are zero-filled by the hardware
+    if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < 1 || p < 8) return false;
     if (n >= 2147483647LL - BK || p >= 2147483647LL - TN) return false;
     CUtensorMap mapA, mapB;
-    make_map(&mapA, X, n, p, TM);
-    make_map(&mapB, X, n, p, TN);
+    make_map(&mapA, X, n, ldx, p, TM);
+    make_map(&mapB, X, n, ldx, p, TN);
     const int nI = (int)((p + TM - 1) / TM), nJ = (int)((p + TN - 1) / TN);
     int ntiles = 0;
     for (int j = 0; j < nJ; j++) ntiles += std::max(0, nI - 2 * j);

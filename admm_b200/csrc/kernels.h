@@ -22,7 +22,7 @@ void gemm(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const 
 // exact_hi = 1 also rewrites the high parts in shared memory (does not rely on the tensor core
 // ignoring the 13 low mantissa bits of its fp32-typed operands).
 // returns false if the shape cannot use the tensor path (caller falls back to gemm<float>)
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 p, float* G, i64 ld, int exact_hi);
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi);
 
 // ---- gemv.cu -----------------------------------------------------------------------------
 // out[j] = sum_i A(i,j) v[i]   (A m x ncol column-major, lda)  -- one dot product per column

@@ -21,8 +21,6 @@
 
 namespace b200 {
 
-namespace {
-
 // DataStd over row shards (a world of one rank degenerates to the plain single-GPU passes).
 // y_dev in place; X_in -> X_out (may alias).  Returns meanY / scaleY on the host.
 struct StdStats {
@@ -93,8 +91,6 @@ void standardize_all(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out,
     if (flag == 1 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.scaleX.data(), d_scaleX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
 }
-
-}  // namespace
 
 void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
                        const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out)
@@ -169,7 +165,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     G.zero(s);
     const char* gram_env = getenv("B200ADMM_GRAM");            // "simt" forces the CUDA-core kernel, "exact" the hi rewrite
     const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
-    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, ldx, p, G.p, ld, (gram_env && !strcmp(gram_env, "exact")) ? 1 : 0);
+    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, (gram_env && !strcmp(gram_env, "exact")) ? 1 : 0);
     if (!on_tensor) {
         // CUDA-core path (shapes the tensor kernel does not take)
         gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);

@@ -48,6 +48,7 @@ void ingest_f64(cudaStream_t s, const void* src, int dtype, size_t count, double
 void add_to_diagonal(cudaStream_t s, float* A, i64 ld, i64 p, float v);
 float coarse_eig_device(cudaStream_t s, const float* S, i64 n, i64 lds, int* nmatvec);
 void spd_inverse_f32(cudaStream_t s, float* a, i64 p, i64 ld, float* W, int* info_host);
+template <class T> void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* keep_factor);
 
 // stdize.cu pieces used by the drivers
 template <class T> void mean_from_sums(cudaStream_t s, const T* sums, i64 p, i64 n_total, T* mean);

@@ -1,0 +1,195 @@
+"""GPU parity tests of the other solvers on the hot path -- wide lasso / elastic net (n <= p),
+row-split consensus lasso, least absolute deviation and basis pursuit -- through the C ABI,
+against the CPU oracle on the same inputs and against the reference's README vectors.
+
+Stated tolerances:
+  float32 paths (wide, consensus): max|dbeta| <= 2e-4 * max(1, |beta|_inf) at the same (X, y, lambda, rho);
+      supports equal except coordinates below 1e-4 in magnitude; iteration totals within 5 %.
+  float64 paths (LAD, BP): max|dbeta| <= 1e-7 (the GPU sums the norms in another order; LAD/BP stop at
+      eps 1e-4, so an iteration more or less would already move beta by ~1e-5 -- counts must agree within 1).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import readme_vectors as R
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LAM = float(np.exp(-2))
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.fixture(scope="module")
+def A():
+    import admm_b200
+    admm_b200.device_info()
+    return admm_b200
+
+
+@pytest.fixture(scope="module")
+def lasso_xy():
+    d = np.load(os.path.join(G, "readme_lasso_data.npz"))
+    return d["x"], d["y"]
+
+
+def dense(beta):
+    return np.asarray(beta.todense())
+
+
+def close(b_gpu, b_cpu, tol, band=1e-4):
+    scale = max(1.0, float(np.abs(b_cpu).max()))
+    assert np.abs(b_gpu - b_cpu).max() <= tol * scale, np.abs(b_gpu - b_cpu).max()
+    mism = (b_gpu != 0) != (b_cpu != 0)
+    if mism.any():
+        assert max(np.abs(b_gpu[mism]).max(), np.abs(b_cpu[mism]).max()) < band
+
+
+def problem(n, p, seed, nsig=8, noise=1.0):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0.0, 2.0, size=(n, p))
+    b = np.zeros(p)
+    b[:nsig] = rng.uniform(0.5, 1.5, size=nsig)
+    y = x @ b + noise * rng.normal(size=n)
+    return np.asfortranarray(x), y, b
+
+
+# ------------------------------------------------------------------------------------------ LAD
+def test_readme_lad(A, O, lasso_xy):
+    x, y = lasso_xy
+    f = A.admm_lad(x, y, intercept=False).fit()
+    o = O.lad(x, y, intercept=False)
+    assert f.beta[0] == 0.0
+    assert abs(f.niter - o["niter"]) <= 1 and abs(f.niter - 443) <= 1
+    assert np.abs(f.beta[1:] - R.LAD_ADMM).max() < 1e-7
+    assert np.abs(f.beta - o["beta"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("n,p,intercept", [(500, 12, True), (2600, 25, True), (2600, 25, False)])
+def test_lad_matches_oracle(A, O, n, p, intercept):
+    rng = np.random.default_rng(n + p)
+    x = np.asfortranarray(rng.normal(1.0, 2.0, size=(n, p)))
+    y = 2.0 + x @ rng.uniform(size=p) + rng.standard_t(3, size=n)
+    f = A.admm_lad(x, y, intercept=intercept).fit()
+    o = O.lad(x, y, intercept=intercept)
+    assert abs(f.niter - o["niter"]) <= 1
+    assert np.abs(f.beta - o["beta"]).max() < 1e-7
+
+
+def test_lad_trace(A, O):
+    from admm_b200 import _capi as K
+    rng = np.random.default_rng(2)
+    x = np.asfortranarray(rng.normal(size=(300, 8)))
+    y = x @ rng.uniform(size=8) + rng.standard_t(3, size=300)
+    with K.trace(which=0, cap=5000) as tr:
+        f = A.admm_lad(x, y).fit()
+    o = O.lad(x, y, trace_cap=5000)
+    m = min(f.niter, o["niter"], 60)
+    assert np.allclose(tr.rows[:m], o["trace"][:m], rtol=1e-8, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ BP
+def test_readme_bp(A, O):
+    d = np.load(os.path.join(G, "readme_bp_data.npz"))
+    f = A.admm_bp(d["x"], d["y"]).fit()
+    o = O.bp(d["x"], d["y"])
+    b = dense(f.beta)[:, 0]
+    diff = d["beta_true"] - b
+    assert abs(f.niter - 72) <= 1
+    assert abs(diff.min() - R.BP_RANGE[0]) < 1e-7 and abs(diff.max() - R.BP_RANGE[1]) < 1e-7
+    assert np.abs(b - o["beta"]).max() < 1e-7
+    assert np.array_equal(b != 0, o["beta"] != 0)
+
+
+def test_bp_recovers_sparse_signal(A, O):
+    rng = np.random.default_rng(5)
+    n, p, k = 120, 500, 12
+    x = np.asfortranarray(rng.normal(size=(n, p)))
+    bt = np.zeros(p)
+    bt[rng.choice(p, k, replace=False)] = rng.uniform(0.5, 1.5, size=k)
+    y = x @ bt
+    f = A.admm_bp(x, y).opts(eps_abs=1e-6, eps_rel=1e-6).fit()
+    o = O.bp(x, y, eps_abs=1e-6, eps_rel=1e-6)
+    b = dense(f.beta)[:, 0]
+    assert abs(f.niter - o["niter"]) <= 1
+    assert np.abs(b - o["beta"]).max() < 1e-7
+    assert np.abs(b - bt).max() < 1e-3                # exact recovery up to the stopping tolerance
+    assert np.abs(x @ b - y).max() < 1e-3             # feasibility A x = b
+
+
+# ------------------------------------------------------------------------------------------ wide
+@pytest.mark.parametrize("n,p,model,alpha", [(100, 400, "lasso", 1.0), (80, 1000, "lasso", 1.0),
+                                             (100, 400, "enet", 0.5), (64, 64, "lasso", 1.0)])
+def test_wide_path_matches_oracle(A, O, n, p, model, alpha):
+    x, y, _ = problem(n, p, seed=n * 7 + p)
+    nl = 12
+    if model == "lasso":
+        f = A.admm_lasso(x, y).penalty(nlambda=nl).fit()
+    else:
+        f = A.admm_enet(x, y).penalty(nlambda=nl, alpha=alpha).fit()
+    o = O.lasso_path(x, y, nlambda=nl, model=model, alpha=alpha)
+    assert np.allclose(f.lambda_, o["lambda_"], rtol=1e-5)
+    assert abs(f.info["eig"] - o["eig"]) < 1e-4 * o["eig"]            # gamma: coarse Lanczos on XX'
+    bg, bc = dense(f.beta), o["beta"]
+    for k in range(nl):
+        close(bg[:, k], bc[:, k], 3e-4)
+    ng, nc = f.niter.astype(int), o["niter"].astype(int)
+    assert abs(ng.sum() - nc.sum()) <= max(5, 0.05 * nc.sum()), (ng, nc)
+
+
+def test_wide_trace(A, O):
+    from admm_b200 import _capi as K
+    x, y, _ = problem(60, 300, seed=17)
+    lam = [0.3]
+    with K.trace(which=0, cap=3000) as tr:
+        f = A.admm_lasso(x, y).penalty(lam).fit()
+    o = O.lasso_path(x, y, lam, trace_lambda=0, trace_cap=3000)
+    m = min(int(f.niter[0]), int(o["niter"][0]), 25)
+    assert m >= 5
+    assert np.allclose(tr.rows[:m], o["trace"][:m], rtol=2e-3, atol=1e-7)   # incl. the adaptive rho column
+
+
+# ------------------------------------------------------------------------------------------ consensus
+def test_readme_parallel_lasso(A, O, lasso_xy):
+    x, y = lasso_xy
+    f = A.admm_lasso(x, y).penalty(LAM).parallel(2).fit()
+    o = O.lasso_path(x, y, [LAM], nthread=2)
+    b = dense(f.beta)[:, 0]
+    assert np.array_equal(b != 0, R.LASSO_PARADMM != 0)
+    assert np.abs(b - R.LASSO_PARADMM).max() < 5e-6
+    assert np.abs(b - o["beta"][:, 0]).max() < 5e-6
+    assert abs(int(f.niter[0]) - 339) <= 3
+
+
+@pytest.mark.parametrize("n,p,N", [(1200, 40, 3), (999, 64, 4), (90, 120, 2)])     # the last one: Woodbury blocks
+def test_consensus_matches_oracle(A, O, n, p, N):
+    x, y, _ = problem(n, p, seed=n + p + N)
+    lam = [0.4, 0.1] if n > p else [0.8, 0.4]
+    f = A.admm_lasso(x, y).penalty(lam).parallel(N).opts(maxit=3000).fit()
+    o = O.lasso_path(x, y, lam, nthread=N, maxit=3000)
+    assert abs(f.info["rho"] - o["rho"]) < 1e-5 * o["rho"]
+    bg, bc = dense(f.beta), o["beta"]
+    for k in range(len(lam)):
+        close(bg[:, k], bc[:, k], 2e-4)
+    ng, nc = f.niter.astype(int), o["niter"].astype(int)
+    assert np.abs(ng - nc).max() <= max(3, 0.05 * nc.max()), (ng, nc)
+
+
+def test_consensus_trace_and_maxit(A, O):
+    from admm_b200 import _capi as K
+    x, y, _ = problem(400, 30, seed=3)
+    with K.trace(which=0, cap=500) as tr:
+        f = A.admm_lasso(x, y).penalty([0.2]).parallel(2).opts(maxit=40).fit()
+    o = O.lasso_path(x, y, [0.2], nthread=2, maxit=40, trace_lambda=0, trace_cap=500)
+    assert int(f.niter[0]) == int(o["niter"][0]) == 41                 # ran out: maxit + 1
+    m = 40
+    assert len(tr.rows) == m
+    assert np.allclose(tr.rows[:m], o["trace"][:m], rtol=2e-3, atol=1e-7)
+    assert np.abs(dense(f.beta)[:, 0] - o["beta"][:, 0]).max() < 1e-5
