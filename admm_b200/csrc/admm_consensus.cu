@@ -230,7 +230,7 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
             b.Kinv.alloc((size_t)p * (size_t)ld);
             b.Kinv.zero(s);
             // (the tensor kernel declines block starts that are not 16-byte aligned; CUDA cores then)
-            const bool on_tensor = want_tensor && gram_tn_tensor(s, A, b.rows, ldx, p, b.Kinv.p, ld, 0);
+            const bool on_tensor = want_tensor && gram_tn_tensor(s, A, b.rows, ldx, p, b.Kinv.p, ld, 1);
             if (!on_tensor)
                 gemm<float>(s, true, false, p, p, b.rows, 1.f, A, ldx, A, ldx, 0.f, b.Kinv.p, ld, GEMM_LOWER | GEMM_MIRROR);
             add_to_diagonal(s, b.Kinv.p, ld, p, frho);

@@ -211,6 +211,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         mbar_wait(smem_u32(tmem_empty + acc.idx), acc.phase ^ 1u);
                         tc_fence_after();
                     }
+                    // odd chunks accumulate -A*B: the accumulator's truncation (round toward zero) then errs
+                    // upward instead of downward, and the bias cancels between neighbouring chunks
+                    const uint32_t idesc = IDESC | ((((ks / CHUNK_STEPS) & 1) != 0) ? (1u << 13) : 0u);
                     mbar_wait(smem_u32(full_raw + r.idx), r.phase);
                     mbar_wait(smem_u32(full_lo + q.idx), q.phase);
                     tc_fence_after();
@@ -221,9 +224,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int sub = 0; sub < BK / 8; sub++) {
                         const uint64_t off = (uint64_t)(sub * 32 >> 4);      // 8 tf32 = 32 bytes along K
-                        tc_mma_tf32(d, a_hi + off, b_hi + off, IDESC, (c > 0 || sub > 0) ? 1u : 0u);
-                        tc_mma_tf32(d, a_lo + off, b_hi + off, IDESC, 1u);
-                        tc_mma_tf32(d, a_hi + off, b_lo + off, IDESC, 1u);
+                        tc_mma_tf32(d, a_hi + off, b_hi + off, idesc, (c > 0 || sub > 0) ? 1u : 0u);
+                        tc_mma_tf32(d, a_lo + off, b_hi + off, idesc, 1u);
+                        tc_mma_tf32(d, a_hi + off, b_lo + off, idesc, 1u);
                     }
                     tc_commit(smem_u32(empty_raw + r.idx));
                     tc_commit(smem_u32(empty_lo + q.idx));
@@ -252,11 +255,26 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     uint4 v;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
                     uint4 h;
-                    h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                    const float lx = __uint_as_float(v.x) - __uint_as_float(h.x);
-                    const float ly = __uint_as_float(v.y) - __uint_as_float(h.y);
-                    const float lz = __uint_as_float(v.z) - __uint_as_float(h.z);
-                    const float lw = __uint_as_float(v.w) - __uint_as_float(h.w);
+                    float lx, ly, lz, lw;
+                    if (exact_hi) {
+                        // round-to-nearest split: hi = rn_tf32(x), lo = rn_tf32(x - hi)  (unbiased, |lo| <= 2^-12 |x|)
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.x) : "f"(__uint_as_float(v.x)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.y) : "f"(__uint_as_float(v.y)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.z) : "f"(__uint_as_float(v.z)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.w) : "f"(__uint_as_float(v.w)));
+                        uint32_t t;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.x) - __uint_as_float(h.x))); lx = __uint_as_float(t);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.y) - __uint_as_float(h.y))); ly = __uint_as_float(t);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.z) - __uint_as_float(h.z))); lz = __uint_as_float(t);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.w) - __uint_as_float(h.w))); lw = __uint_as_float(t);
+                    } else {
+                        // truncation split: the tensor core ignores the 13 low bits, so the raw tile serves as hi
+                        h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+                        lx = __uint_as_float(v.x) - __uint_as_float(h.x);
+                        ly = __uint_as_float(v.y) - __uint_as_float(h.y);
+                        lz = __uint_as_float(v.z) - __uint_as_float(h.z);
+                        lw = __uint_as_float(v.w) - __uint_as_float(h.w);
+                    }
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(dst + off), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
                     if (exact_hi)
                         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(src + off), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
@@ -290,7 +308,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tc_ld32(taddr, v);
                     tc_wait_ld();
 #pragma unroll
-                    for (int c = 0; c < 32; c++) sum[cg * 32 + c] += __uint_as_float(v[c]);
+                    for (int c = 0; c < 32; c++) {
+                        if (ch & 1) sum[cg * 32 + c] -= __uint_as_float(v[c]);      // odd chunks hold -A*B
+                        else sum[cg * 32 + c] += __uint_as_float(v[c]);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(smem_u32(tmem_empty + acc.idx));

@@ -163,9 +163,9 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, XY.p);
     allreduce_sum(s, XY.p, p);
     G.zero(s);
-    const char* gram_env = getenv("B200ADMM_GRAM");            // "simt" forces the CUDA-core kernel, "exact" the hi rewrite
+    const char* gram_env = getenv("B200ADMM_GRAM");            // "simt": CUDA-core kernel; "trunc": truncation split
     const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
-    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, (gram_env && !strcmp(gram_env, "exact")) ? 1 : 0);
+    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, (gram_env && !strcmp(gram_env, "trunc")) ? 0 : 1);
     if (!on_tensor) {
         // CUDA-core path (shapes the tensor kernel does not take)
         gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
