@@ -109,27 +109,28 @@ def test_readme_bp(A, O):
 
 
 def test_bp_recovers_sparse_signal(A, O):
-    """Same iterates as the CPU restatement (trace), sparse signal recovered to the stopping tolerance.
-    BP's adaptive rho makes the late iterations sensitive to last-bit differences in the norms, so the
-    final count is compared loosely and the first 40 iterations tightly."""
+    """Same iterates as the CPU restatement over the whole run (trace), sparse signal recovered to the
+    stopping tolerance.  (Instances whose first iterations sit exactly on the restart rule
+    c < 0.999 c_old -- e.g. seed 5 of this generator -- branch differently on a last-bit difference of a
+    norm and are not usable as parity cases; seeds 6 and 7 are not on that edge.)"""
     from admm_b200 import _capi as K
-    rng = np.random.default_rng(5)
-    n, p, k = 120, 500, 12
-    x = np.asfortranarray(rng.normal(size=(n, p)))
-    bt = np.zeros(p)
-    bt[rng.choice(p, k, replace=False)] = rng.uniform(0.5, 1.5, size=k)
-    y = x @ bt
-    with K.trace(which=0, cap=2000) as tr:
-        f = A.admm_bp(x, y).fit()
-    o = O.bp(x, y, trace_cap=2000)
-    b = dense(f.beta)[:, 0]
-    m = min(f.niter, o["niter"], 40)
-    assert np.allclose(tr.rows[:m, [0, 1, 2, 4]], o["trace"][:m][:, [0, 1, 2, 4]], rtol=1e-7, atol=1e-12)
-    assert np.allclose(tr.rows[:m, 3], o["trace"][:m, 3], rtol=1e-6, atol=1e-10)
-    assert abs(f.niter - o["niter"]) <= 0.2 * o["niter"]
-    assert np.abs(b - o["beta"]).max() < 1e-2          # both stop at eps = 1e-4 (relative), at different iterations
-    assert np.abs(b - bt).max() < 1e-2
-    assert np.abs(x @ b - y).max() < 5e-2
+    for seed in (6, 7):
+        rng = np.random.default_rng(seed)
+        n, p, k = 120, 500, 12
+        x = np.asfortranarray(rng.normal(size=(n, p)))
+        bt = np.zeros(p)
+        bt[rng.choice(p, k, replace=False)] = rng.uniform(0.5, 1.5, size=k)
+        y = x @ bt
+        with K.trace(which=0, cap=2000) as tr:
+            f = A.admm_bp(x, y).fit()
+        o = O.bp(x, y, trace_cap=2000)
+        b = dense(f.beta)[:, 0]
+        assert f.niter == o["niter"]
+        assert np.allclose(tr.rows, o["trace"][:o["niter"]], rtol=1e-7, atol=1e-12)
+        assert np.abs(b - o["beta"]).max() < 1e-8
+        assert np.array_equal(b != 0, o["beta"] != 0)      # support bit-exact
+        assert np.abs(b - bt).max() < 1e-2                 # recovered to the (relative 1e-4) stopping tolerance
+        assert np.abs(x @ b - y).max() < 5e-2
 
 
 # ------------------------------------------------------------------------------------------ wide
@@ -199,5 +200,6 @@ def test_consensus_trace_and_maxit(A, O):
     assert int(f.niter[0]) == int(o["niter"][0]) == 41                 # ran out: maxit + 1
     m = 40
     assert len(tr.rows) == m
-    assert np.allclose(tr.rows[:m], o["trace"][:m], rtol=2e-3, atol=1e-7)
+    assert np.allclose(tr.rows[:m, [0, 1, 2, 4]], o["trace"][:m][:, [0, 1, 2, 4]], rtol=1e-4, atol=1e-7)
+    assert np.allclose(tr.rows[:m, 3], o["trace"][:m, 3], rtol=1e-2, atol=1e-6)   # rho*sqrt(N)*|z+ - z|: float differences of nearly equal z
     assert np.abs(dense(f.beta)[:, 0] - o["beta"][:, 0]).max() < 1e-5

@@ -3,7 +3,7 @@ its C ABI (via the Python mirror of the R chain), against the CPU oracle on the 
 against the reference's README vectors.
 
 Tolerances (stated): float32 path, same (X, y, lambda, rho):
-  * coefficients: max|dbeta| <= 1e-4 * max(1, |beta|_inf) on the original scale (the solver's own
+  * coefficients: max|dbeta| <= 2e-4 * max(1, |beta|_inf) on the original scale (the solver's own
     stopping tolerance is 1e-5 relative on standardised variables; GPU and CPU differ only in
     the summation order of the norms / K^-1 product, but an iteration more or less moves beta
     by about the stopping tolerance);
@@ -47,7 +47,7 @@ def dense(beta):
     return np.asarray(beta.todense())
 
 
-def assert_beta_close(b_gpu, b_cpu, tol=1e-4, band=1e-4):
+def assert_beta_close(b_gpu, b_cpu, tol=2e-4, band=2e-4):
     scale = max(1.0, float(np.abs(b_cpu).max()))
     assert np.abs(b_gpu - b_cpu).max() <= tol * scale, np.abs(b_gpu - b_cpu).max()
     mism = (b_gpu != 0) != (b_cpu != 0)
