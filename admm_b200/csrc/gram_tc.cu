@@ -269,11 +269,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.w) - __uint_as_float(h.w))); lw = __uint_as_float(t);
                     } else {
                         // truncation split: the tensor core ignores the 13 low bits, so the raw tile serves as hi
+                        // (lo itself is rounded to nearest TF32 so that the hardware's truncation of it is a no-op)
                         h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                        lx = __uint_as_float(v.x) - __uint_as_float(h.x);
-                        ly = __uint_as_float(v.y) - __uint_as_float(h.y);
-                        lz = __uint_as_float(v.z) - __uint_as_float(h.z);
-                        lw = __uint_as_float(v.w) - __uint_as_float(h.w);
+                        uint32_t t;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.x) - __uint_as_float(h.x))); lx = __uint_as_float(t);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.y) - __uint_as_float(h.y))); ly = __uint_as_float(t);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.z) - __uint_as_float(h.z))); lz = __uint_as_float(t);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.w) - __uint_as_float(h.w))); lw = __uint_as_float(t);
                     }
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(dst + off), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
                     if (exact_hi)
