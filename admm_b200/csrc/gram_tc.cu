@@ -15,38 +15,41 @@
 // each chunk is accumulated in TMEM from zero (48 MMAs) and then added, with round-to-nearest fp32
 // adds on the CUDA cores, to per-thread register accumulators that live for the whole tile.
 //
-// Kernel anatomy (one persistent CTA per SM, 512 threads, tile = 128 x 256 of G, k-slice = 16):
-//   warp 0      TMA producer: X tile pairs (A: 128 columns, B: 256 columns, 16 rows of X each,
-//               K-major, SWIZZLE_64B) into a 6-deep shared-memory ring, mbarrier complete_tx.
+// Kernel anatomy (one persistent CTA per SM, 512 threads, tile = 128 x 192 of G, k-slice = 32):
+//   warp 0      TMA producer: X tile pairs (A: 128 columns, B: 192 columns, 32 rows of X each,
+//               K-major, SWIZZLE_128B) into a 3-deep shared-memory ring, mbarrier complete_tx.
 //   warps 4-7   splitter: hi/lo split of each landed stage.  The split is element-wise, so it is
-//               independent of the swizzle: lo goes to a 3-deep ring with the same layout; the raw
+//               independent of the swizzle: lo goes to a 2-deep ring with the same layout; the raw
 //               buffer is used as `hi` directly (the tensor core ignores the 13 low bits) or is
 //               overwritten with hi (exact_hi = 1).  fence.proxy.async + mbarrier arrive.
-//   warp 1      MMA issuer (one elected lane): 2 k-sub-steps x 3 tcgen05.mma per stage into one of
-//               two 256-column TMEM accumulators; tcgen05.commit frees the rings / publishes a chunk.
-//   warps 8-15  epilogue (setmaxnreg 192): per chunk tcgen05.ld 32x32b.x32 -> fp32 add into 128
-//               accumulator registers per thread; per tile one coalesced store of the 128 x 256 block
+//   warp 1      MMA issuer (one elected lane): 4 k-sub-steps x 3 tcgen05.mma per stage into one of
+//               two 192-column TMEM accumulators; tcgen05.commit frees the rings / publishes a chunk.
+//   warps 8-15  epilogue (setmaxnreg 192): per chunk tcgen05.ld 32x32b.x32 -> fp32 add into 96
+//               accumulator registers per thread; per tile one coalesced store of the 128 x 192 block
 //               (column-major: the 32 lanes of a warp hit 32 consecutive rows = one 128-byte line).
 // Only tiles that touch the lower triangle are computed; a final pass mirrors it.
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda.h>
+#include <cstring>
+#include <cstdlib>
 
 namespace b200 {
 
 namespace {
 
 constexpr int TM = 128;          // G rows per tile  (A operand: TM columns of X)
-constexpr int TN = 256;          // G cols per tile  (B operand: TN columns of X)
-constexpr int BK = 16;           // rows of X per pipeline stage (64 bytes: one SWIZZLE_64B row)
-constexpr int RAW_STAGES = 6;
-constexpr int LO_STAGES = 3;
-constexpr int A_BYTES = TM * BK * 4;             // 8192
-constexpr int B_BYTES = TN * BK * 4;             // 16384
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 24576
-constexpr int CHUNK_STEPS = 8;                   // k-steps per TMEM accumulation chunk (128 rows, 48 MMAs)
+constexpr int TN = 192;          // G cols per tile  (B operand: TN columns of X)
+constexpr int BK = 32;           // rows of X per pipeline stage (128 bytes: one SWIZZLE_128B row; 64-byte
+                                 // rows halve the TMA / L2 request efficiency -- measured)
+constexpr int RAW_STAGES = 3;
+constexpr int LO_STAGES = 2;
+constexpr int A_BYTES = TM * BK * 4;             // 16384
+constexpr int B_BYTES = TN * BK * 4;             // 24576
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 40960
+constexpr int CHUNK_STEPS = 4;                   // stages per TMEM accumulation chunk (128 rows, 48 MMAs)
 constexpr int GT_THREADS = 512;
-constexpr int SPLIT_THREADS = 128, EPI_THREADS = 256;
+constexpr int SPLIT_THREADS = 160, EPI_THREADS = 256;        // splitter: warps 3-7
 constexpr int SMEM_BYTES = (RAW_STAGES + LO_STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -75,6 +78,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
+}
+// wait with back-off: for consumers whose wake-up latency does not matter (the epilogue waits
+// thousands of cycles per chunk) -- a tight try_wait loop would steal issue slots from the warps
+// that feed the tensor core
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
 {
@@ -111,18 +131,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_64B shared-memory operand descriptor (rows of 64 bytes, 8-row groups 512 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr)
+// K-major, SWIZZLE_128B shared-memory operand descriptor (rows of 128 bytes, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr)
 {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, 16-byte units
     d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset between 8-row groups
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-    d |= (uint64_t)4 << 61;                          // layout type: SWIZZLE_64B
+    d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
     return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 192
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 struct Ring {
@@ -131,21 +151,23 @@ struct Ring {
     __device__ __forceinline__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1u; } }
 };
 
-// tile t (0-based) of the lower-triangle cover -> (I, J); tiles of block column J are I = 2J .. nI-1
+// tile t (0-based) of the lower-triangle cover -> (I, J).  Block column J (TN columns) needs the row
+// blocks I (TM rows) whose last row reaches its first column: I >= floor(TN * J / TM).
+__host__ __device__ __forceinline__ int first_row_block(int j) { return (TN * j) / TM; }
 __device__ __forceinline__ void tile_coords(int t, int nI, int& I, int& J)
 {
     int j = 0;
     for (;;) {
-        const int cnt = nI - 2 * j;
+        const int cnt = nI - first_row_block(j);
         if (t < cnt) break;
         t -= cnt; j++;
     }
-    J = j; I = 2 * j + t;
+    J = j; I = first_row_block(j) + t;
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               float* __restrict__ G, int p, long long ld, int nk, int nI, int ntiles, int exact_hi)
+               float* __restrict__ G, int p, long long ld, int nk, int nI, int ntiles, int exact_hi, int dbg)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -219,12 +241,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(acc.idx * TN);
                     const uint32_t ra = smem_u32(raw + r.idx * STAGE_BYTES), la = smem_u32(lo + q.idx * STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_sw64(ra), b_hi = umma_desc_sw64(ra + A_BYTES);
-                    const uint64_t a_lo = umma_desc_sw64(la), b_lo = umma_desc_sw64(la + A_BYTES);
+                    const uint64_t a_hi = umma_desc_k(ra), b_hi = umma_desc_k(ra + A_BYTES);
+                    const uint64_t a_lo = umma_desc_k(la), b_lo = umma_desc_k(la + A_BYTES);
 #pragma unroll
                     for (int sub = 0; sub < BK / 8; sub++) {
                         const uint64_t off = (uint64_t)(sub * 32 >> 4);      // 8 tf32 = 32 bytes along K
+                        if (dbg & 2) continue;                               // timing experiment: no tensor work
                         tc_mma_tf32(d, a_hi + off, b_hi + off, idesc, (c > 0 || sub > 0) ? 1u : 0u);
+                        if (dbg & 4) continue;                               // timing experiment: single pass
                         tc_mma_tf32(d, a_lo + off, b_hi + off, idesc, 1u);
                         tc_mma_tf32(d, a_hi + off, b_lo + off, idesc, 1u);
                     }
@@ -239,9 +263,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 3 && warp < 8) {
         // ================================ hi / lo splitter ============================
-        const int st = threadIdx.x - 128;
+        const int st = threadIdx.x - 96;
         Ring r, q;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             for (int ks = 0; ks < nk; ks++) {
@@ -250,33 +274,27 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t src = smem_u32(raw + r.idx * STAGE_BYTES) + (uint32_t)st * 16u;
                 const uint32_t dst = smem_u32(lo + q.idx * STAGE_BYTES) + (uint32_t)st * 16u;
 #pragma unroll 4
-                for (int i = 0; i < STAGE_BYTES / 16 / SPLIT_THREADS; i++) {
+                for (int i = 0; i < ((dbg & 1) ? 0 : STAGE_BYTES / 16 / SPLIT_THREADS); i++) {
                     const uint32_t off = (uint32_t)i * (SPLIT_THREADS * 16u);
                     uint4 v;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
                     uint4 h;
                     float lx, ly, lz, lw;
+                    // round-to-nearest to TF32 precision (10 mantissa bits) with integer ALU ops: add half an ulp of
+                    // the kept part, clear the 13 dropped bits (ties away from zero, like cvt.rna.tf32; the
+                    // conversion instruction itself runs at a fraction of the ALU rate and throttled this warp)
+                    auto rn = [](uint32_t b) { return (b + 0x1000u) & 0xFFFFE000u; };
                     if (exact_hi) {
-                        // round-to-nearest split: hi = rn_tf32(x), lo = rn_tf32(x - hi)  (unbiased, |lo| <= 2^-12 |x|)
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.x) : "f"(__uint_as_float(v.x)));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.y) : "f"(__uint_as_float(v.y)));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.z) : "f"(__uint_as_float(v.z)));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h.w) : "f"(__uint_as_float(v.w)));
-                        uint32_t t;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.x) - __uint_as_float(h.x))); lx = __uint_as_float(t);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.y) - __uint_as_float(h.y))); ly = __uint_as_float(t);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.z) - __uint_as_float(h.z))); lz = __uint_as_float(t);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.w) - __uint_as_float(h.w))); lw = __uint_as_float(t);
+                        // hi = rn_tf32(x), lo = rn_tf32(x - hi)  (unbiased, |lo| <= 2^-11 |x|)
+                        h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
                     } else {
                         // truncation split: the tensor core ignores the 13 low bits, so the raw tile serves as hi
-                        // (lo itself is rounded to nearest TF32 so that the hardware's truncation of it is a no-op)
                         h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                        uint32_t t;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.x) - __uint_as_float(h.x))); lx = __uint_as_float(t);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.y) - __uint_as_float(h.y))); ly = __uint_as_float(t);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.z) - __uint_as_float(h.z))); lz = __uint_as_float(t);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__uint_as_float(v.w) - __uint_as_float(h.w))); lw = __uint_as_float(t);
                     }
+                    lx = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x))));
+                    ly = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y))));
+                    lz = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z))));
+                    lw = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w))));
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(dst + off), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
                     if (exact_hi)
                         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(src + off), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
@@ -291,7 +309,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================================ epilogue ====================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;" ::: "memory");
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
-        const int half = (warp - 8) >> 2;                  // which 128 of the 256 accumulator columns
+        const int half = (warp - 8) >> 2;                  // which 96 of the 192 accumulator columns
         Ring acc;
         float sum[TN / 2];
 #pragma unroll
@@ -301,10 +319,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tile_coords(t, nI, I, J);
             const int row = I * TM + quad * 32 + lane;
             for (int ch = 0; ch < nchunk; ch++) {
-                mbar_wait(smem_u32(tmem_full + acc.idx), acc.phase);
+                mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
                 tc_fence_after();
 #pragma unroll
-                for (int cg = 0; cg < TN / 2 / 32; cg++) {
+                for (int cg = 0; cg < TN / 2 / 32; cg++) {       // 96 columns = 3 x 32
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc.idx * TN + half * (TN / 2) + cg * 32);
                     tc_ld32(taddr, v);
@@ -380,7 +398,7 @@ void make_map(CUtensorMap* m, const float* X, i64 n, i64 ldx, i64 p, int box_col
     cuuint32_t box[2] = { (cuuint32_t)BK, (cuuint32_t)box_cols };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
@@ -390,24 +408,27 @@ void make_map(CUtensorMap* m, const float* X, i64 n, i64 ldx, i64 p, int box_col
 // Writes the full symmetric p x p matrix into G (leading dimension ld).
 bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi)
 {
-    // TMA: 16-byte aligned base and column stride; rows beyond n are zero-filled by the hardware
+    // 16-byte aligned base and column stride (TMA / 128-bit loads); rows beyond n are zero-filled
     if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < 1 || p < 8) return false;
     if (n >= 2147483647LL - BK || p >= 2147483647LL - TN) return false;
-    CUtensorMap mapA, mapB;
-    make_map(&mapA, X, n, ldx, p, TM);
-    make_map(&mapB, X, n, ldx, p, TN);
     const int nI = (int)((p + TM - 1) / TM), nJ = (int)((p + TN - 1) / TN);
     int ntiles = 0;
-    for (int j = 0; j < nJ; j++) ntiles += std::max(0, nI - 2 * j);
+    for (int j = 0; j < nJ; j++) ntiles += std::max(0, nI - first_row_block(j));
     const int nk = (int)((n + BK - 1) / BK);
-    static bool attr = false;
-    if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr = true;
-    }
     const int grid = std::min(ntiles, sm_count());
-    gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, nI, ntiles, exact_hi);
-    KERNEL_CHECK();
+    {
+        CUtensorMap mapA, mapB;
+        make_map(&mapA, X, n, ldx, p, TM);
+        make_map(&mapB, X, n, ldx, p, TN);
+        static bool attr = false;
+        if (!attr) {
+            CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr = true;
+        }
+        const char* dbg_env = getenv("B200ADMM_GRAM_DBG");     // timing experiments only (results are wrong when set)
+        gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, nI, ntiles, exact_hi ? 1 : 0, dbg_env ? atoi(dbg_env) : 0);
+        KERNEL_CHECK();
+    }
     dim3 mg((unsigned)((p + 31) / 32), (unsigned)((p + 31) / 32));
     mirror_lower_kernel<<<mg, 256, 0, s>>>(G, (int)p, (long long)ld);
     KERNEL_CHECK();
