@@ -59,6 +59,13 @@ Context& ctx()
     return c;
 }
 
+cudaStream_t copy_stream()
+{
+    Context& c = ctx();
+    if (!c.copy) CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    return c.copy;
+}
+
 TraceRequest& trace_request()
 {
     static TraceRequest t;

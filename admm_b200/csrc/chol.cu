@@ -26,18 +26,23 @@ constexpr int DIAG_THREADS = 512;
 
 // Factor the kb x kb diagonal block at A (lda) in shared memory; write L11 back (lower part)
 // and inv(L11) (lower triangular, zeros above) to Dinv (kb x kb, ld = NB).
+// Right-looking, all 512 threads on the rank-1 update (2-D mapping: no integer division, no idle
+// upper half); the block inverse is then built column by column -- thread c runs the forward
+// substitution L w = e_c with its column of the inverse held in shared memory (float) or, when two
+// NB x NB tiles do not fit (double), in the output buffer.
 template <class T>
-__global__ void __launch_bounds__(DIAG_THREADS) chol_diag_kernel(T* __restrict__ A, i64 lda, int kb, int k0, T* __restrict__ Dinv, int* info)
+__global__ void __launch_bounds__(DIAG_THREADS) chol_diag_kernel(T* __restrict__ A, i64 lda, int kb, int k0, T* __restrict__ Dinv, int* info, int winv_in_smem)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);            // S[c * LDS + r], column-major, LDS = NB + 1
     constexpr int LDS = NB + 1;
+    T* Wm = S + NB * LDS;                              // inverse, same layout (only if winv_in_smem)
     const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;            // 32 x 16
 
-    for (int idx = tid; idx < kb * kb; idx += DIAG_THREADS) {
-        const int r = idx % kb, c = idx / kb;
-        S[c * LDS + r] = (r >= c) ? A[(i64)r + (i64)c * lda] : T(0);
-    }
+    for (int c = ty; c < kb; c += DIAG_THREADS / 32)
+        for (int r = tx; r < kb; r += 32)
+            S[c * LDS + r] = (r >= c) ? A[(i64)r + (i64)c * lda] : T(0);
     __syncthreads();
 
     for (int j = 0; j < kb; j++) {
@@ -50,33 +55,49 @@ __global__ void __launch_bounds__(DIAG_THREADS) chol_diag_kernel(T* __restrict__
         const T piv = S[j * LDS + j];
         for (int r = j + 1 + tid; r < kb; r += DIAG_THREADS) S[j * LDS + r] = S[j * LDS + r] / piv;
         __syncthreads();
-        // trailing update of the lower triangle: S(r,c) -= S(r,j) * S(c,j), j < c <= r
-        const int m = kb - j - 1;
-        for (int idx = tid; idx < m * m; idx += DIAG_THREADS) {
-            const int r = j + 1 + idx % m, c = j + 1 + idx / m;
-            if (r >= c) S[c * LDS + r] -= S[j * LDS + r] * S[j * LDS + c];
+        // S(r,c) -= S(r,j) * S(c,j) for j < c <= r < kb
+        for (int c = j + 1 + ty; c < kb; c += DIAG_THREADS / 32) {
+            const T lc = S[j * LDS + c];
+            for (int r = c + tx; r < kb; r += 32) S[c * LDS + r] -= S[j * LDS + r] * lc;
         }
         __syncthreads();
     }
 
-    for (int idx = tid; idx < kb * kb; idx += DIAG_THREADS) {
-        const int r = idx % kb, c = idx / kb;
-        if (r >= c) A[(i64)r + (i64)c * lda] = S[c * LDS + r];
-    }
-    // inverse of the lower-triangular block: thread c solves L w = e_c by forward substitution
-    for (int c = tid; c < kb; c += DIAG_THREADS) {
-        T* w = Dinv + (i64)c * NB;
-        for (int r = 0; r < c; r++) w[r] = T(0);
-        w[c] = T(1) / S[c * LDS + c];
-        for (int r = c + 1; r < kb; r++) {
-            T acc = T(0);
-            for (int k = c; k < r; k++) acc += S[k * LDS + r] * w[k];
-            w[r] = -acc / S[r * LDS + r];
+    for (int c = ty; c < kb; c += DIAG_THREADS / 32)
+        for (int r = c + tx; r < kb; r += 32) A[(i64)r + (i64)c * lda] = S[c * LDS + r];
+
+    // inverse of the lower-triangular block
+    if (winv_in_smem) {
+        for (int c = tid; c < kb; c += DIAG_THREADS) {
+            T* w = Wm + c * LDS;
+            w[c] = T(1) / S[c * LDS + c];
+            for (int r = c + 1; r < kb; r++) {
+                T acc0 = T(0), acc1 = T(0);
+                int k = c;
+                for (; k + 1 < r; k += 2) { acc0 += S[k * LDS + r] * w[k]; acc1 += S[(k + 1) * LDS + r] * w[k + 1]; }
+                if (k < r) acc0 += S[k * LDS + r] * w[k];
+                w[r] = -(acc0 + acc1) / S[r * LDS + r];
+            }
         }
-        for (int r = kb; r < NB; r++) w[r] = T(0);
+        __syncthreads();
+        for (int c = ty; c < NB; c += DIAG_THREADS / 32)
+            for (int r = tx; r < NB; r += 32)
+                Dinv[(i64)c * NB + r] = (c < kb && r < kb && r >= c) ? Wm[c * LDS + r] : T(0);
+    } else {
+        for (int c = tid; c < kb; c += DIAG_THREADS) {
+            T* w = Dinv + (i64)c * NB;
+            for (int r = 0; r < c; r++) w[r] = T(0);
+            w[c] = T(1) / S[c * LDS + c];
+            for (int r = c + 1; r < kb; r++) {
+                T acc = T(0);
+                for (int k = c; k < r; k++) acc += S[k * LDS + r] * w[k];
+                w[r] = -acc / S[r * LDS + r];
+            }
+            for (int r = kb; r < NB; r++) w[r] = T(0);
+        }
+        for (int c = kb + tid; c < NB; c += DIAG_THREADS)
+            for (int r = 0; r < NB; r++) Dinv[(i64)c * NB + r] = T(0);
     }
-    for (int c = kb + tid; c < NB; c += DIAG_THREADS)
-        for (int r = 0; r < NB; r++) Dinv[(i64)c * NB + r] = T(0);
 }
 
 template <class T>
@@ -140,7 +161,8 @@ void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev)
     const i64 nblk = (p + NB - 1) / NB;
     T* Dinv = work;
     T* panel = work + nblk * NB * NB;
-    const size_t smem = sizeof(T) * NB * (NB + 1);
+    const int winv_in_smem = sizeof(T) == 4 ? 1 : 0;             // two 128 x 129 tiles: 132 KB in float, too large in double
+    const size_t smem = sizeof(T) * NB * (NB + 1) * (winv_in_smem ? 2 : 1);
     static bool attr_done_f = false, attr_done_d = false;
     bool& done = std::is_same<T, float>::value ? attr_done_f : attr_done_d;
     if (!done) {
@@ -152,7 +174,7 @@ void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev)
         const i64 k0 = b * NB;
         const int kb = (int)std::min<i64>(NB, p - k0);
         T* Akk = A + k0 + k0 * lda;
-        chol_diag_kernel<T><<<1, DIAG_THREADS, smem, s>>>(Akk, lda, kb, (int)k0, Dinv + b * NB * NB, info_dev);
+        chol_diag_kernel<T><<<1, DIAG_THREADS, smem, s>>>(Akk, lda, kb, (int)k0, Dinv + b * NB * NB, info_dev, winv_in_smem);
         KERNEL_CHECK();
         const i64 m = p - k0 - kb;
         if (m <= 0) break;
@@ -197,7 +219,15 @@ void gram_of_lower(cudaStream_t s, const T* W, i64 p, i64 ldw, T* Kinv, i64 ldk)
     gemm<T>(s, true, false, p, p, p, T(1), W, ldw, W, ldw, T(0), Kinv, ldk,
             GEMM_LOWER | GEMM_MIRROR | GEMM_AT_LOWER_TRI | GEMM_B_LOWER_TRI);
 }
-template void gram_of_lower<float>(cudaStream_t, const float*, i64, i64, float*, i64);
+// float: W'W is a Gram matrix of a K-major operand -- the tcgen05 3xTF32 kernel takes it as is
+// (W is stored with explicit zeros above the diagonal)
+template <>
+void gram_of_lower<float>(cudaStream_t s, const float* W, i64 p, i64 ldw, float* Kinv, i64 ldk)
+{
+    if (p >= 512 && gram_tn_tensor(s, W, p, ldw, p, Kinv, ldk, 1)) return;
+    gemm<float>(s, true, false, p, p, p, 1.f, W, ldw, W, ldw, 0.f, Kinv, ldk,
+                GEMM_LOWER | GEMM_MIRROR | GEMM_AT_LOWER_TRI | GEMM_B_LOWER_TRI);
+}
 template void gram_of_lower<double>(cudaStream_t, const double*, i64, i64, double*, i64);
 
 template <class T>

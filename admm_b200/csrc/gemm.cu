@@ -17,16 +17,17 @@
 
 namespace b200 {
 
+struct CfgLarge { static constexpr int BM = 128, BN = 128, BK = 16, V = 4; };   // 8 x 8 outputs per thread
+struct CfgSmall { static constexpr int BM = 64,  BN = 64,  BK = 16, V = 2; };   // 4 x 4 outputs per thread
 template <class T> struct GemmCfg;
-template <> struct GemmCfg<float>  { static constexpr int BM = 128, BN = 128, BK = 16, V = 4; };
-template <> struct GemmCfg<double> { static constexpr int BM = 64,  BN = 64,  BK = 16, V = 2; };
+template <> struct GemmCfg<float>  { typedef CfgLarge Large; typedef CfgSmall Small; };
+template <> struct GemmCfg<double> { typedef CfgSmall Large; typedef CfgSmall Small; };
 
-template <class T, bool TA, bool TB>
+template <class T, class Cfg, bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, T alpha, const T* __restrict__ A, i64 lda,
             const T* __restrict__ B, i64 ldb, T beta, T* __restrict__ C, i64 ldc, int mode)
 {
-    typedef GemmCfg<T> Cfg;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, V = Cfg::V;
     constexpr int PAD = 4;
     constexpr int LA = BM * BK / 256, LB = BN * BK / 256;   // elements each thread stages
@@ -149,18 +150,30 @@ gemm_kernel(int M, int N, int K, T alpha, const T* __restrict__ A, i64 lda,
     }
 }
 
+template <class T, class Cfg>
+static void gemm_launch(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const T* A, i64 lda,
+                        const T* B, i64 ldb, T beta, T* C, i64 ldc, int mode)
+{
+    dim3 grid((unsigned)((M + Cfg::BM - 1) / Cfg::BM), (unsigned)((N + Cfg::BN - 1) / Cfg::BN));
+    if (!ta && !tb) gemm_kernel<T, Cfg, false, false><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else if (!ta && tb) gemm_kernel<T, Cfg, false, true><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else if (ta && !tb) gemm_kernel<T, Cfg, true, false><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else gemm_kernel<T, Cfg, true, true><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    KERNEL_CHECK();
+}
+
 template <class T>
 void gemm(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const T* A, i64 lda,
           const T* B, i64 ldb, T beta, T* C, i64 ldc, int mode)
 {
     if (M <= 0 || N <= 0) return;
-    typedef GemmCfg<T> Cfg;
-    dim3 grid((unsigned)((M + Cfg::BM - 1) / Cfg::BM), (unsigned)((N + Cfg::BN - 1) / Cfg::BN));
-    if (!ta && !tb) gemm_kernel<T, false, false><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    else if (!ta && tb) gemm_kernel<T, false, true><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    else if (ta && !tb) gemm_kernel<T, true, false><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    else gemm_kernel<T, true, true><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    KERNEL_CHECK();
+    typedef typename GemmCfg<T>::Large L;
+    typedef typename GemmCfg<T>::Small S;
+    // narrow or small outputs (panels of the factorisation / triangular inverse): the large tile would
+    // leave most SMs idle, so fall back to the 64 x 64 tile when the large-tile grid cannot fill the chip
+    const i64 big_tiles = ((M + L::BM - 1) / L::BM) * ((N + L::BN - 1) / L::BN);
+    if (big_tiles < 2 * (i64)sm_count()) gemm_launch<T, S>(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else gemm_launch<T, L>(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
 }
 
 template void gemm<float>(cudaStream_t, bool, bool, i64, i64, i64, float, const float*, i64, const float*, i64, float, float*, i64, int);

@@ -151,23 +151,25 @@ struct Ring {
     __device__ __forceinline__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1u; } }
 };
 
-// tile t (0-based) of the lower-triangle cover -> (I, J).  Block column J (TN columns) needs the row
-// blocks I (TM rows) whose last row reaches its first column: I >= floor(TN * J / TM).
-__host__ __device__ __forceinline__ int first_row_block(int j) { return (TN * j) / TM; }
-__device__ __forceinline__ void tile_coords(int t, int nI, int& I, int& J)
+// Tiles are enumerated row block by row block (I-major): row block I (TM rows of G = TM columns of X)
+// needs the column blocks J (TN columns) whose first column does not exceed its last row:
+// J <= floor((TM * I + TM - 1) / TN).  A launch covers the row blocks [I0, I1), so the Gram matrix can
+// be built panel by panel while later columns of X are still being copied to the device.
+__host__ __device__ __forceinline__ int col_blocks_of(int i) { return (TM * i + TM - 1) / TN + 1; }
+__device__ __forceinline__ void tile_coords(int t, int I0, int nJ, int& I, int& J)
 {
-    int j = 0;
+    int i = I0;
     for (;;) {
-        const int cnt = nI - first_row_block(j);
+        const int cnt = min(nJ, col_blocks_of(i));
         if (t < cnt) break;
-        t -= cnt; j++;
+        t -= cnt; i++;
     }
-    J = j; I = first_row_block(j) + t;
+    I = i; J = t;
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               float* __restrict__ G, int p, long long ld, int nk, int nI, int ntiles, int exact_hi, int dbg)
+               float* __restrict__ G, int p, long long ld, int nk, int I0, int nJ, int ntiles, int exact_hi, int dbg)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -210,7 +212,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             Ring r;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 int I, J;
-                tile_coords(t, nI, I, J);
+                tile_coords(t, I0, nJ, I, J);
                 for (int ks = 0; ks < nk; ks++) {
                     mbar_wait(smem_u32(empty_raw + r.idx), r.phase ^ 1u);
                     const uint32_t fb = smem_u32(full_raw + r.idx);
@@ -316,7 +318,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int c = 0; c < TN / 2; c++) sum[c] = 0.f;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             int I, J;
-            tile_coords(t, nI, I, J);
+            tile_coords(t, I0, nJ, I, J);
             const int row = I * TM + quad * 32 + lane;
             for (int ch = 0; ch < nchunk; ch++) {
                 mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
@@ -406,17 +408,21 @@ void make_map(CUtensorMap* m, const float* X, i64 n, i64 ldx, i64 p, int box_col
 }  // namespace
 
 // Writes the full symmetric p x p matrix into G (leading dimension ld).
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi)
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi,
+                    i64 col_begin, i64 col_end, bool mirror)
 {
-    // 16-byte aligned base and column stride (TMA / 128-bit loads); rows beyond n are zero-filled
+    // 16-byte aligned base and column stride (TMA); rows beyond n are zero-filled by the hardware
     if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < 1 || p < 8) return false;
     if (n >= 2147483647LL - BK || p >= 2147483647LL - TN) return false;
-    const int nI = (int)((p + TM - 1) / TM), nJ = (int)((p + TN - 1) / TN);
+    if (col_end < 0) col_end = p;
+    if (col_begin % TM != 0 || (col_end % TM != 0 && col_end != p)) return false;     // panels are whole row blocks
+    const int nJ = (int)((p + TN - 1) / TN);
+    const int I0 = (int)(col_begin / TM), I1 = (int)((col_end + TM - 1) / TM);
     int ntiles = 0;
-    for (int j = 0; j < nJ; j++) ntiles += std::max(0, nI - first_row_block(j));
+    for (int i = I0; i < I1; i++) ntiles += std::min(nJ, col_blocks_of(i));
     const int nk = (int)((n + BK - 1) / BK);
-    const int grid = std::min(ntiles, sm_count());
-    {
+    if (ntiles > 0) {
+        const int grid = std::min(ntiles, sm_count());
         CUtensorMap mapA, mapB;
         make_map(&mapA, X, n, ldx, p, TM);
         make_map(&mapB, X, n, ldx, p, TN);
@@ -426,12 +432,14 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
             attr = true;
         }
         const char* dbg_env = getenv("B200ADMM_GRAM_DBG");     // timing experiments only (results are wrong when set)
-        gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, nI, ntiles, exact_hi ? 1 : 0, dbg_env ? atoi(dbg_env) : 0);
+        gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, I0, nJ, ntiles, exact_hi ? 1 : 0, dbg_env ? atoi(dbg_env) : 0);
         KERNEL_CHECK();
     }
-    dim3 mg((unsigned)((p + 31) / 32), (unsigned)((p + 31) / 32));
-    mirror_lower_kernel<<<mg, 256, 0, s>>>(G, (int)p, (long long)ld);
-    KERNEL_CHECK();
+    if (mirror) {
+        dim3 mg((unsigned)((p + 31) / 32), (unsigned)((p + 31) / 32));
+        mirror_lower_kernel<<<mg, 256, 0, s>>>(G, (int)p, (long long)ld);
+        KERNEL_CHECK();
+    }
     return true;
 }
 

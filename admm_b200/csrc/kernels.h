@@ -22,7 +22,10 @@ void gemm(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const 
 // exact_hi = 1 also rewrites the high parts in shared memory (does not rely on the tensor core
 // ignoring the 13 low mantissa bits of its fp32-typed operands).
 // returns false if the shape cannot use the tensor path (caller falls back to gemm<float>)
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi);
+// [col_begin, col_end): only the row blocks of G belonging to these columns of X are computed (they need
+// columns 0 .. col_end of X); mirror = false defers the lower -> upper copy to the last panel.
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi,
+                    i64 col_begin = 0, i64 col_end = -1, bool mirror = true);
 
 // ---- gemv.cu -----------------------------------------------------------------------------
 // out[j] = sum_i A(i,j) v[i]   (A m x ncol column-major, lda)  -- one dot product per column

@@ -28,68 +28,85 @@ struct StdStats {
     float meanY = 0.f, scaleY = 1.f;
 };
 
+// y in place; returns meanY / scaleY on the host (one small synchronising read)
+static void standardize_y_sharded(cudaStream_t s, float* y, i64 n_local, i64 n_total, int flag, StdStats& st)
+{
+    if (flag == 0) return;
+    DevBuf<float> tmp(4);
+    float* ys = tmp.p;          // [0] sum / mean, [1] sumsq / scale
+    column_sums<float>(s, y, n_local, 1, n_local, ys);
+    allreduce_sum(s, ys, 1);
+    mean_from_sums<float>(s, ys, 1, n_total, ys);                       // ys[0] = mean(y)
+    column_center_sumsq<float>(s, y, n_local, 1, n_local, ys, ys + 1, false);
+    allreduce_sum(s, ys + 1, 1);
+    if (flag == 1) {
+        scale_from_sumsq<float>(s, ys + 1, 1, n_total, true, ys + 1, nullptr);
+        column_apply<float>(s, y, y, n_local, 1, n_local, n_local, nullptr, nullptr, ys + 1);   // y /= scaleY (not centred)
+    } else {
+        scale_from_sumsq<float>(s, ys + 1, 1, n_total, false, ys + 1, nullptr);
+        column_apply<float>(s, y, y, n_local, 1, n_local, n_local, ys, nullptr, ys + 1);        // (y - mean) / scaleY
+    }
+    float h[2];
+    CUDA_CHECK(cudaMemcpyAsync(h, ys, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    st.meanY = (flag == 1) ? 0.f : h[0];
+    st.scaleY = h[1];
+}
+
+// a panel of columns: X_in -> X_out (may alias); d_meanX / d_scaleX / tmp point at the panel's entries
+// (tmp: 2 * pc floats).  Device work only, no host synchronisation.
+static void standardize_cols_sharded(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out, i64 ld_out, i64 n_local, i64 n_total,
+                                     i64 pc, int flag, float* d_meanX, float* d_scaleX, float* tmp)
+{
+    float* sums = tmp;
+    float* inv = tmp + pc;
+    switch (flag) {
+    case 1:
+        column_sums<float>(s, X_in, n_local, pc, ld_in, sums);
+        allreduce_sum(s, sums, pc);
+        mean_from_sums<float>(s, sums, pc, n_total, sums);
+        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, pc, ld_in, sums, d_scaleX, false);
+        allreduce_sum(s, d_scaleX, pc);
+        scale_from_sumsq<float>(s, d_scaleX, pc, n_total, true, d_scaleX, inv);
+        column_apply<float>(s, X_in, X_out, n_local, pc, ld_in, ld_out, nullptr, inv, nullptr);
+        break;
+    case 2:
+        column_sums<float>(s, X_in, n_local, pc, ld_in, sums);
+        allreduce_sum(s, sums, pc);
+        mean_from_sums<float>(s, sums, pc, n_total, d_meanX);
+        column_apply<float>(s, X_in, X_out, n_local, pc, ld_in, ld_out, d_meanX, nullptr, nullptr);
+        break;
+    case 3:
+        column_sums<float>(s, X_in, n_local, pc, ld_in, sums);
+        allreduce_sum(s, sums, pc);
+        mean_from_sums<float>(s, sums, pc, n_total, d_meanX);
+        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, pc, ld_in, d_meanX, d_scaleX, false);
+        allreduce_sum(s, d_scaleX, pc);
+        scale_from_sumsq<float>(s, d_scaleX, pc, n_total, false, d_scaleX, inv);
+        column_apply<float>(s, X_in, X_out, n_local, pc, ld_in, ld_out, d_meanX, inv, nullptr);
+        break;
+    default:
+        if (X_in != X_out) column_apply<float>(s, X_in, X_out, n_local, pc, ld_in, ld_out, nullptr, nullptr, nullptr);
+        break;
+    }
+}
+
+static void fetch_std_stats(cudaStream_t s, i64 p, int flag, const float* d_meanX, const float* d_scaleX, StdStats& st)
+{
+    st.meanX.assign(p, 0.f);
+    st.scaleX.assign(p, 1.f);
+    if (flag == 2 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.meanX.data(), d_meanX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (flag == 1 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.scaleX.data(), d_scaleX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 void standardize_all(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out, i64 ld_out, float* y, i64 n_local, i64 n_total, i64 p,
                      int flag, float* d_meanX, float* d_scaleX, StdStats& st)
 {
     DevBuf<float> tmp(2 * p + 8);
-    float* sums = tmp.p;
-    float* inv = tmp.p + p;
-    float* ys = tmp.p + 2 * p;          // [0] sum / mean, [1] sumsq / scale
-    // ---- y
-    if (flag != 0) {
-        column_sums<float>(s, y, n_local, 1, n_local, ys);
-        allreduce_sum(s, ys, 1);
-        mean_from_sums<float>(s, ys, 1, n_total, ys);                       // ys[0] = mean(y)
-        column_center_sumsq<float>(s, y, n_local, 1, n_local, ys, ys + 1, false);
-        allreduce_sum(s, ys + 1, 1);
-        if (flag == 1) {
-            scale_from_sumsq<float>(s, ys + 1, 1, n_total, true, ys + 1, nullptr);
-            column_apply<float>(s, y, y, n_local, 1, n_local, n_local, nullptr, nullptr, ys + 1);   // y /= scaleY (not centred)
-        } else {
-            scale_from_sumsq<float>(s, ys + 1, 1, n_total, false, ys + 1, nullptr);
-            column_apply<float>(s, y, y, n_local, 1, n_local, n_local, ys, nullptr, ys + 1);        // (y - mean) / scaleY
-        }
-        float h[2];
-        CUDA_CHECK(cudaMemcpyAsync(h, ys, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        st.meanY = (flag == 1) ? 0.f : h[0];
-        st.scaleY = h[1];
-    }
-    // ---- X
-    st.meanX.assign(p, 0.f);
-    st.scaleX.assign(p, 1.f);
-    switch (flag) {
-    case 1:
-        column_sums<float>(s, X_in, n_local, p, ld_in, sums);
-        allreduce_sum(s, sums, p);
-        mean_from_sums<float>(s, sums, p, n_total, sums);
-        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, ld_in, sums, d_scaleX, false);
-        allreduce_sum(s, d_scaleX, p);
-        scale_from_sumsq<float>(s, d_scaleX, p, n_total, true, d_scaleX, inv);
-        column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, nullptr, inv, nullptr);
-        break;
-    case 2:
-        column_sums<float>(s, X_in, n_local, p, ld_in, sums);
-        allreduce_sum(s, sums, p);
-        mean_from_sums<float>(s, sums, p, n_total, d_meanX);
-        column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, d_meanX, nullptr, nullptr);
-        break;
-    case 3:
-        column_sums<float>(s, X_in, n_local, p, ld_in, sums);
-        allreduce_sum(s, sums, p);
-        mean_from_sums<float>(s, sums, p, n_total, d_meanX);
-        column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, p, ld_in, d_meanX, d_scaleX, false);
-        allreduce_sum(s, d_scaleX, p);
-        scale_from_sumsq<float>(s, d_scaleX, p, n_total, false, d_scaleX, inv);
-        column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, d_meanX, inv, nullptr);
-        break;
-    default:
-        if (X_in != X_out) column_apply<float>(s, X_in, X_out, n_local, p, ld_in, ld_out, nullptr, nullptr, nullptr);
-        break;
-    }
-    if (flag == 2 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.meanX.data(), d_meanX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (flag == 1 || flag == 3) CUDA_CHECK(cudaMemcpyAsync(st.scaleX.data(), d_scaleX, p * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    standardize_y_sharded(s, y, n_local, n_total, flag, st);
+    standardize_cols_sharded(s, X_in, ld_in, X_out, ld_out, n_local, n_total, p, flag, d_meanX, d_scaleX, tmp.p);
+    fetch_std_stats(s, p, flag, d_meanX, d_scaleX, st);
 }
 
 void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
@@ -125,12 +142,82 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     b200admm_timing T;
     memset(&T, 0, sizeof T);
 
+    const i64 ldx = (n_local + 3) & ~(i64)3;
+    const bool padded = ldx != n_local;
+    const char* gram_env = getenv("B200ADMM_GRAM");            // "simt": CUDA-core kernel; "trunc": truncation split
+    const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
+    const int split_mode = (gram_env && !strcmp(gram_env, "trunc")) ? 0 : 1;
+    DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
+    DevBuf<float> d_meanX(p), d_scaleX(p);
+    DevBuf<float> XY(ld);
+    DevBuf<float> G((size_t)p * (size_t)ld);
+    StdStats st;
+    const bool host_input = d->dtype == B200ADMM_F32_HOST || d->dtype == B200ADMM_F64_HOST;
+    const char* pipe_env = getenv("B200ADMM_PIPELINE");
+    const bool pipelined = host_input && !cm.active() && want_tensor && p >= 1024 && !(pipe_env && !strcmp(pipe_env, "0"));
+
+    if (pipelined) {
+        // ---- host input: copy, DataStd, X'y and the Gram matrix pipelined over column panels --------------
+        // Columns are standardised independently and row block I of G needs only columns 0 .. 128 (I + 1),
+        // so panel k is copied on a second stream while panels < k are standardised and their row blocks
+        // of G are computed.  After the last panel lands only its own share of the Gram work remains.
+        tm.start();
+        if (padded) Xs.zero(s);
+        XY.zero(s);
+        G.zero(s);
+        ingest_f32(s, d->y, d->dtype, (size_t)n_local, ys.p);
+        standardize_y_sharded(s, ys.p, n_local, n, flag, st);
+        const size_t esz = d->dtype == B200ADMM_F64_HOST ? 8 : 4;
+        i64 pw = (i64)(((size_t)3 << 30) / ((size_t)n_local * esz));          // ~3 GB of host data per panel
+        if (const char* pw_env = getenv("B200ADMM_PANEL_COLS")) pw = atoll(pw_env);     // tests: force several panels
+        pw = std::max<i64>(128, (pw / 128) * 128);
+        const int npan = (int)((p + pw - 1) / pw);
+        DevBuf<float> tmp(2 * pw + 8);
+        DevBuf<double> slab[2];
+        if (esz == 8) { slab[0].alloc((size_t)n_local * (size_t)pw); slab[1].alloc((size_t)n_local * (size_t)pw); }
+        std::vector<cudaEvent_t> landed(npan), freed(2);
+        for (auto& e : landed) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : freed) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cudaStream_t cs = copy_stream();
+        cudaEvent_t start_ev;
+        CUDA_CHECK(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(start_ev, s));
+        CUDA_CHECK(cudaStreamWaitEvent(cs, start_ev, 0));
+        for (int k = 0; k < npan; k++) {
+            const i64 c0 = k * pw, pc = std::min(pw, p - c0);
+            float* dstp = Xs.p + c0 * ldx;
+            if (esz == 4) {
+                const float* src = (const float*)d->x + c0 * n_local;
+                if (!padded) CUDA_CHECK(cudaMemcpyAsync(dstp, src, (size_t)n_local * pc * 4, cudaMemcpyHostToDevice, cs));
+                else CUDA_CHECK(cudaMemcpy2DAsync(dstp, ldx * 4, src, n_local * 4, n_local * 4, pc, cudaMemcpyHostToDevice, cs));
+            } else {
+                const double* src = (const double*)d->x + c0 * n_local;
+                if (k >= 2) CUDA_CHECK(cudaStreamWaitEvent(cs, freed[k & 1], 0));
+                CUDA_CHECK(cudaMemcpyAsync(slab[k & 1].p, src, (size_t)n_local * pc * 8, cudaMemcpyHostToDevice, cs));
+            }
+            CUDA_CHECK(cudaEventRecord(landed[k], cs));
+            CUDA_CHECK(cudaStreamWaitEvent(s, landed[k], 0));
+            if (esz == 8) {
+                if (!padded) convert_f64_to_f32(s, slab[k & 1].p, dstp, (size_t)n_local * pc);
+                else for (i64 j = 0; j < pc; j++) convert_f64_to_f32(s, slab[k & 1].p + j * n_local, dstp + j * ldx, (size_t)n_local);
+                CUDA_CHECK(cudaEventRecord(freed[k & 1], s));
+            }
+            standardize_cols_sharded(s, dstp, ldx, dstp, ldx, n_local, n, pc, flag, d_meanX.p + c0, d_scaleX.p + c0, tmp.p);
+            gemv_t<float>(s, dstp, n_local, pc, ldx, ys.p, XY.p + c0);
+            if (!gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode, c0, c0 + pc, k == npan - 1))
+                throw CudaError("pipelined Gram: tensor kernel declined the shape");
+        }
+        fetch_std_stats(s, p, flag, d_meanX.p, d_scaleX.p, st);
+        T.gram = tm.stop();                                   // copy + DataStd + X'y + Gram, overlapped
+        CUDA_CHECK(cudaStreamSynchronize(cs));
+        for (auto& e : landed) cudaEventDestroy(e);
+        for (auto& e : freed) cudaEventDestroy(e);
+        cudaEventDestroy(start_ev);
+        T.ingest = 0; T.standardize = 0;
+    } else {
     // ---- ingest ------------------------------------------------------------------------------
     // The standardised copy keeps a leading dimension that is a multiple of 4 (zero pad rows) so
     // that the TMA descriptor of the tensor-core Gram kernel can address it for any n.
-    const i64 ldx = (n_local + 3) & ~(i64)3;
-    const bool padded = ldx != n_local;
-    DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
     const float* X_in = Xs.p;
     i64 ld_in = ldx;
     tm.start();
@@ -148,32 +235,28 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     T.ingest = tm.stop();
 
     // ---- DataStd -----------------------------------------------------------------------------
-    DevBuf<float> d_meanX(p), d_scaleX(p);
-    StdStats st;
     tm.start();
     standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
     T.standardize = tm.stop();
     Xtmp.release();
 
     // ---- X'y, lambda0, Gram ------------------------------------------------------------------
-    DevBuf<float> XY(ld);
-    DevBuf<float> G((size_t)p * (size_t)ld);
     tm.start();
     XY.zero(s);
     gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, XY.p);
     allreduce_sum(s, XY.p, p);
     G.zero(s);
-    const char* gram_env = getenv("B200ADMM_GRAM");            // "simt": CUDA-core kernel; "trunc": truncation split
-    const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
-    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, (gram_env && !strcmp(gram_env, "trunc")) ? 0 : 1);
+    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode);
     if (!on_tensor) {
         // CUDA-core path (shapes the tensor kernel does not take)
         gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
     }
     allreduce_sum(s, G.p, (size_t)p * (size_t)ld);
+    T.gram = tm.stop();
+    }
     std::vector<float> h_xy(p);
     CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), XY.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
-    T.gram = tm.stop();
+    CUDA_CHECK(cudaStreamSynchronize(s));
     Xs.release();                                       // the tall solver never touches X again
     ys.release();
 

@@ -10,8 +10,10 @@ struct Context {
     bool ready = false;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy = nullptr;     // second stream for host->device copies overlapped with compute
 };
-Context& ctx();                      // throws CodeError(B200ADMM_ENODEVICE) when no B200 is usable
+Context& ctx();
+cudaStream_t copy_stream();                      // throws CodeError(B200ADMM_ENODEVICE) when no B200 is usable
 
 struct TraceRequest {
     double* buf = nullptr;
