@@ -59,6 +59,60 @@ Context& ctx()
     return c;
 }
 
+// ---- exact-size recycling of large device blocks ---------------------------------------------
+namespace {
+struct CachedBlock { void* p; size_t bytes; };
+std::vector<CachedBlock>& block_cache() { static std::vector<CachedBlock> c; return c; }
+std::mutex& cache_mutex() { static std::mutex m; return m; }
+constexpr size_t CACHE_MIN_BYTES = (size_t)64 << 20;
+bool cache_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("B200ADMM_CACHE"); on = (e && !strcmp(e, "0")) ? 0 : 1; }
+    return on == 1;
+}
+}  // namespace
+
+void dev_cache_release()
+{
+    std::lock_guard<std::mutex> g(cache_mutex());
+    for (auto& b : block_cache()) cudaFree(b.p);
+    block_cache().clear();
+}
+
+void* dev_alloc(size_t bytes)
+{
+    if (bytes >= CACHE_MIN_BYTES && cache_enabled()) {
+        std::lock_guard<std::mutex> g(cache_mutex());
+        auto& c = block_cache();
+        for (size_t i = 0; i < c.size(); i++)
+            if (c[i].bytes == bytes) { void* p = c[i].p; c.erase(c.begin() + i); return p; }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // make room: drop everything we are holding on to, retry once
+        cudaGetLastError();
+        dev_cache_release();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw CodeError(B200ADMM_ENOMEM, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    return p;
+}
+
+void dev_free(void* p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes >= CACHE_MIN_BYTES && cache_enabled()) {
+        std::lock_guard<std::mutex> g(cache_mutex());
+        auto& c = block_cache();
+        if (c.size() < 16) { c.push_back({p, bytes}); return; }
+    }
+    cudaFree(p);
+}
+
 cudaStream_t copy_stream()
 {
     Context& c = ctx();
@@ -315,6 +369,7 @@ extern "C" {
 const char* b200admm_last_error(void) { return g_last_error.c_str(); }
 int b200admm_version(void) { return B200ADMM_VERSION; }
 unsigned long long b200admm_launch_count(void) { return g_launch_count; }
+void b200admm_release_cache(void) { dev_cache_release(); }
 void* b200admm_stream(void)
 {
     void* h = nullptr;

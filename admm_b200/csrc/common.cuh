@@ -35,6 +35,12 @@ extern unsigned long long g_launch_count;       // kernels launched by this libr
 #define KERNEL_CHECK() do { ++::b200::g_launch_count; ::b200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); } while (0)
 
 // ------------------------------------------------------------------ device buffers
+// Large blocks (>= 64 MB) are recycled between calls through a small exact-size cache (capi.cu):
+// cudaMalloc / cudaFree of the 40 GB working copy cost ~0.1 s per fit otherwise.
+void* dev_alloc(size_t bytes);
+void dev_free(void* p, size_t bytes);
+void dev_cache_release();
+
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -47,11 +53,11 @@ template <class T> struct DevBuf {
     {
         release();
         n = n_;
-        if (n) CUDA_CHECK(cudaMalloc((void**)&p, n * sizeof(T)));
+        if (n) p = (T*)dev_alloc(n * sizeof(T));
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) dev_free(p, n * sizeof(T));
         p = nullptr; n = 0;
     }
     void zero(cudaStream_t s) { if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }

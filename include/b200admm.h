@@ -147,6 +147,10 @@ unsigned long long b200admm_launch_count(void);
 /* the cudaStream_t every kernel of this library is launched on (for event timing by the host
  * program); NULL if no device is usable */
 void* b200admm_stream(void);
+/* Device blocks of 64 MB and more (the float32 working copy of x, the p x p matrices) are kept for
+ * reuse by the next call instead of being returned to the driver; this frees them.
+ * Environment B200ADMM_CACHE=0 disables the recycling altogether. */
+void b200admm_release_cache(void);
 /* name, SM count and total memory of the current device; returns B200ADMM_ENODEVICE if none */
 int  b200admm_device_info(char* name, int name_len, int* sm_count, int64_t* mem_bytes);
 
