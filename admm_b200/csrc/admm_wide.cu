@@ -245,6 +245,24 @@ inline void balance_rho(double& rho, double rp, double ep, double rd, double ed)
     if (rd < ed) rho *= 1.2;
 }
 
+// Y (cols x rows, column-major, leading dimension ldy) = X' for X (rows x cols, ldx): 32 x 32 tiles
+// through shared memory, coalesced on both sides
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ X, i64 rows, i64 cols, i64 ldx, float* __restrict__ Y, i64 ldy)
+{
+    __shared__ float tile[32][33];
+    const i64 r0 = (i64)blockIdx.x * 32, c0 = (i64)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int c = ty; c < 32; c += 8) {
+        const i64 r = r0 + tx, cc = c0 + c;
+        tile[c][tx] = (r < rows && cc < cols) ? X[r + cc * ldx] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const i64 cc = c0 + tx, rr = r0 + r;
+        if (cc < cols && rr < rows) Y[cc + rr * ldy] = tile[tx][r];
+    }
+}
+
 // C (n x n, full) = X X' accumulated over column chunks so that no float sum runs over more than
 // 8192 terms before it is folded into C (keeps the float32 result unbiased for p ~ 1e6)
 void gram_nt_chunked(cudaStream_t s, const float* X, i64 n, i64 p, i64 ldx, float* C)
@@ -311,7 +329,24 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     float sprad = 0.f;
     {
         DevBuf<float> Gn((size_t)n * (size_t)n);
-        gram_nt_chunked(s, X, n, p, ldx, Gn.p);
+        // XX' is the Gram matrix of Y = X' (p x n, its columns are the rows of X): transposing once turns
+        // the product into the K-major shape the tcgen05 3xTF32 kernel takes (fp32-accurate, ~5x the
+        // CUDA-core rate); shapes it declines fall back to the chunked CUDA-core product
+        bool on_tensor = false;
+        const char* gram_env = getenv("B200ADMM_GRAM");
+        if (!(gram_env && !strcmp(gram_env, "simt")) && n >= 8) {
+            const i64 ldy = (p + 3) & ~(i64)3;
+            DevBuf<float> Y((size_t)ldy * (size_t)n);
+            if (ldy != p) Y.zero(s);
+            dim3 tg((unsigned)((n + 31) / 32), (unsigned)((p + 31) / 32));
+            if (tg.y <= 65535) {
+                transpose_kernel<<<tg, 256, 0, s>>>(X, n, p, ldx, Y.p, ldy);
+                KERNEL_CHECK();
+                on_tensor = gram_tn_tensor(s, Y.p, p, ldy, n, Gn.p, n, 1);
+                CUDA_CHECK(cudaStreamSynchronize(s));
+            }
+        }
+        if (!on_tensor) gram_nt_chunked(s, X, n, p, ldx, Gn.p);
         T.gram = tm.stop();
         tm.start();
         sprad = coarse_eig_device(s, Gn.p, n, n, nullptr);

@@ -126,6 +126,12 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(const T* __restrict__ A, i6
         if (i < m) {
             const T* a = A + i + jb * lda;
             int j = 0;
+            for (; j + 8 <= cnt; j += 8) {          // eight independent column loads in flight per thread
+                T a0 = a[(i64)j * lda], a1 = a[(i64)(j + 1) * lda], a2 = a[(i64)(j + 2) * lda], a3 = a[(i64)(j + 3) * lda];
+                T a4 = a[(i64)(j + 4) * lda], a5 = a[(i64)(j + 5) * lda], a6 = a[(i64)(j + 6) * lda], a7 = a[(i64)(j + 7) * lda];
+                s0 += a0 * vs[j]; s1 += a1 * vs[j + 1]; s2 += a2 * vs[j + 2]; s3 += a3 * vs[j + 3];
+                s0 += a4 * vs[j + 4]; s1 += a5 * vs[j + 5]; s2 += a6 * vs[j + 6]; s3 += a7 * vs[j + 7];
+            }
             for (; j + 4 <= cnt; j += 4) {
                 const T a0 = a[(i64)j * lda], a1 = a[(i64)(j + 1) * lda], a2 = a[(i64)(j + 2) * lda], a3 = a[(i64)(j + 3) * lda];
                 s0 += a0 * vs[j]; s1 += a1 * vs[j + 1]; s2 += a2 * vs[j + 2]; s3 += a3 * vs[j + 3];
