@@ -334,7 +334,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
         // CUDA-core rate); shapes it declines fall back to the chunked CUDA-core product
         bool on_tensor = false;
         const char* gram_env = getenv("B200ADMM_GRAM");
-        if (!(gram_env && !strcmp(gram_env, "simt")) && n >= 8) {
+        if (!(gram_env && !strcmp(gram_env, "simt")) && n >= 512) {      // small problems: plain fp32 product
             const i64 ldy = (p + 3) & ~(i64)3;
             DevBuf<float> Y((size_t)ldy * (size_t)n);
             if (ldy != p) Y.zero(s);

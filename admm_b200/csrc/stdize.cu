@@ -114,7 +114,7 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = (float)in[i];
 }
 
-inline unsigned col_grid(i64 p) { return (unsigned)std::min<i64>(p, (i64)sm_count() * 4); }
+inline unsigned col_grid(i64 p) { return (unsigned)std::min<i64>(p, (i64)1 << 20); }   // one CTA per column, dynamic scheduling
 
 }  // namespace
 

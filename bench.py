@@ -291,7 +291,12 @@ def main():
         "phase_s": T,
         "roofline": {"kernel": "tall_path_kernel (persistent lambda-path iteration kernel)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     # dram__bytes_read + write of this kernel from the committed ncu --set full capture
+                     # (profiles/r1a_tall_path_kernel_ncu_raw.csv: 343.68 GB for a 1064-iteration launch = 323.0 MB
+                     # per iteration, below the 400.7 MB algorithmic figure because the alternating sweep
+                     # direction leaves the tail of K^-1 in L2), scaled to this launch's iteration count
+                     "traffic": (323.0e6 * niter_path) if (p == 10000) else None, "traffic_unit": "bytes per launch (one launch = the whole lambda path)",
+                     "peak_source": peak_src,
                      "bytes_per_iteration": bpi, "us_per_iteration": T["iterate"] / max(niter_path, 1) * 1e6},
         "setup_flops": {"gram_syrk_flop": gram_flops, "gram_tflops": gram_flops / world / max(T["gram"], 1e-9) / 1e12},
         "clocks": clocks, "gpu_launches": int(launches), "device": info["name"],
