@@ -357,6 +357,260 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// =================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster share one 256 x 256 tile of G.
+// CTA r of the pair stages its own 128 rows of the A operand and its own half (128 of 256 columns)
+// of the B operand; the leader's single MMA thread issues M = 256, N = 256 instructions that read A
+// and half of B from each CTA's shared memory and write each CTA's 128 accumulator rows into its
+// own TMEM.  Per CTA and per 32-row stage this moves 32 KB through TMA / the splitter instead of
+// 40 KB and the tensor core reads 8 KB instead of 10 KB of operands per MMA, for 2.7x the work --
+// the shared-memory data pipe (the measured limiter of the 1-CTA kernel) stops being the bound, and
+// the L2 / DRAM traffic per output element drops by 1.6x.
+//   per CTA:  warp 0 TMA producer (local barriers)      warp 1 MMA issuer (leader CTA only)
+//             warp 2 TMEM alloc (cta_group::2)           warps 3-7 hi / lo splitter
+//             warps 8-15 epilogue (128 accumulator registers per thread)
+// Cross-CTA signalling: splitter and epilogue threads of both CTAs arrive on the LEADER's mbarriers
+// (mapa + mbarrier.arrive.release.cluster); tcgen05.commit multicasts to both CTAs' barriers.
+// =================================================================================================
+constexpr int T2 = 256;                              // pair tile edge
+constexpr int P2_A_BYTES = 128 * BK * 4;             // 16 KB: this CTA's 128 rows of A
+constexpr int P2_B_BYTES = 128 * BK * 4;             // 16 KB: this CTA's half of B
+constexpr int P2_STAGE = P2_A_BYTES + P2_B_BYTES;    // 32 KB
+constexpr int P2_RAW = 4, P2_LO = 2;
+constexpr int P2_SMEM = (P2_RAW + P2_LO) * P2_STAGE + 1024 + 256;
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2 >> 3) << 17) | ((uint32_t)(T2 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// wait on a local barrier whose arrivals come from both CTAs of the pair (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" :: "r"(local_bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// pair tiles, row block by row block: row block I (256 rows) needs column blocks J = 0 .. I
+__device__ __forceinline__ void pair_tile_coords(int t, int I0, int& I, int& J)
+{
+    int i = I0;
+    for (;;) {
+        const int cnt = i + 1;
+        if (t < cnt) break;
+        t -= cnt; i++;
+    }
+    I = i; J = t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+gram_pair_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* raw = base;
+    unsigned char* lo = base + P2_RAW * P2_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lo + P2_LO * P2_STAGE);
+    uint64_t* full_raw = bars;                        // [P2_RAW]  local: TMA -> splitter
+    uint64_t* empty_raw = bars + P2_RAW;              // [P2_RAW]  MMA commit (multicast) -> TMA
+    uint64_t* full_lo = bars + 2 * P2_RAW;            // [P2_LO]   leader's: splitters of both CTAs -> MMA
+    uint64_t* empty_lo = full_lo + P2_LO;             // [P2_LO]   MMA commit (multicast) -> splitter
+    uint64_t* tmem_full = empty_lo + P2_LO;           // [2]       MMA commit (multicast) -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;             // [2]       leader's: epilogues of both CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P2_RAW; i++) { mbar_init(smem_u32(full_raw + i), 1); mbar_init(smem_u32(empty_raw + i), 1); }
+        for (int i = 0; i < P2_LO; i++) { mbar_init(smem_u32(full_lo + i), 2 * SPLIT_THREADS); mbar_init(smem_u32(empty_lo + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(tmem_full + i), 1); mbar_init(smem_u32(tmem_empty + i), 2 * EPI_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                               // barriers of both CTAs are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nchunk = (nk + CHUNK_STEPS - 1) / CHUNK_STEPS;
+
+    if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+
+    if (warp == 0) {
+        // ================================ TMA producer (each CTA, local) ================
+        if (lane == 0) {
+            Ring r;
+            for (int t = pair; t < ntiles; t += npairs) {
+                int I, J;
+                pair_tile_coords(t, I0, I, J);
+                for (int ks = 0; ks < nk; ks++) {
+                    mbar_wait(smem_u32(empty_raw + r.idx), r.phase ^ 1u);
+                    const uint32_t fb = smem_u32(full_raw + r.idx);
+                    mbar_expect_tx(fb, P2_STAGE);
+                    const uint32_t dst = smem_u32(raw + r.idx * P2_STAGE);
+                    tma_load_2d(dst, &map, ks * BK, I * T2 + (int)rank * 128, fb);
+                    tma_load_2d(dst + P2_A_BYTES, &map, ks * BK, J * T2 + (int)rank * 128, fb);
+                    r.advance(P2_RAW);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ================
+        if (rank == 0 && lane == 0) {
+            Ring r, q, acc;
+            for (int t = pair; t < ntiles; t += npairs) {
+                for (int ks = 0; ks < nk; ks++) {
+                    const int c = ks % CHUNK_STEPS;
+                    if (c == 0) {
+                        mbar_wait_cluster(smem_u32(tmem_empty + acc.idx), acc.phase ^ 1u);
+                        tc_fence_after();
+                    }
+                    mbar_wait_cluster(smem_u32(full_lo + q.idx), q.phase);  // both CTAs' hi and lo planes are in place
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(acc.idx * T2);
+                    const uint32_t ra = smem_u32(raw + r.idx * P2_STAGE), la = smem_u32(lo + q.idx * P2_STAGE);
+                    const uint64_t a_hi = umma_desc_k(ra), b_hi = umma_desc_k(ra + P2_A_BYTES);
+                    const uint64_t a_lo = umma_desc_k(la), b_lo = umma_desc_k(la + P2_A_BYTES);
+#pragma unroll
+                    for (int sub = 0; sub < BK / 8; sub++) {
+                        const uint64_t off = (uint64_t)(sub * 32 >> 4);
+                        tc_mma_tf32_pair(d, a_hi + off, b_hi + off, IDESC2, (c > 0 || sub > 0) ? 1u : 0u);
+                        tc_mma_tf32_pair(d, a_lo + off, b_hi + off, IDESC2, 1u);
+                        tc_mma_tf32_pair(d, a_hi + off, b_lo + off, IDESC2, 1u);
+                    }
+                    tc_commit_pair(smem_u32(empty_raw + r.idx));
+                    tc_commit_pair(smem_u32(empty_lo + q.idx));
+                    if (c == CHUNK_STEPS - 1 || ks == nk - 1) {
+                        tc_commit_pair(smem_u32(tmem_full + acc.idx));
+                        acc.advance(2);
+                    }
+                    r.advance(P2_RAW);
+                    q.advance(P2_LO);
+                }
+            }
+        }
+    } else if (warp >= 3 && warp < 8) {
+        // ================================ hi / lo splitter (each CTA) ==================
+        const int st = threadIdx.x - 96;
+        Ring r, q;
+        for (int t = pair; t < ntiles; t += npairs) {
+            for (int ks = 0; ks < nk; ks++) {
+                mbar_wait(smem_u32(full_raw + r.idx), r.phase);
+                mbar_wait(smem_u32(empty_lo + q.idx), q.phase ^ 1u);
+                const uint32_t src = smem_u32(raw + r.idx * P2_STAGE);
+                const uint32_t dst = smem_u32(lo + q.idx * P2_STAGE);
+#pragma unroll 4
+                for (int e = st; e < P2_STAGE / 16; e += SPLIT_THREADS) {
+                    const uint32_t off = (uint32_t)e * 16u;
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
+                    auto rn = [](uint32_t b) { return (b + 0x1000u) & 0xFFFFE000u; };
+                    uint4 h;
+                    h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
+                    const float lx = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x))));
+                    const float ly = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y))));
+                    const float lz = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z))));
+                    const float lw = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w))));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(dst + off), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(src + off), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
+                }
+                fence_proxy_async();
+                mbar_arrive_cluster(smem_u32(full_lo + q.idx), 0);              // the leader's barrier
+                r.advance(P2_RAW);
+                q.advance(P2_LO);
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================ epilogue (each CTA: its 128 rows) =============
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;" ::: "memory");
+        const int quad = warp & 3;
+        const int half = (warp - 8) >> 2;                  // which 128 of the 256 accumulator columns
+        Ring acc;
+        float sum[T2 / 2];
+#pragma unroll
+        for (int c = 0; c < T2 / 2; c++) sum[c] = 0.f;
+        for (int t = pair; t < ntiles; t += npairs) {
+            int I, J;
+            pair_tile_coords(t, I0, I, J);
+            const int row = I * T2 + (int)rank * 128 + quad * 32 + lane;
+            for (int ch = 0; ch < nchunk; ch++) {
+                mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
+                tc_fence_after();
+#pragma unroll
+                for (int cg = 0; cg < T2 / 2 / 32; cg++) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc.idx * T2 + half * (T2 / 2) + cg * 32);
+                    tc_ld32(taddr, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; c++) sum[cg * 32 + c] += __uint_as_float(v[c]);
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(smem_u32(tmem_empty + acc.idx), 0);         // the leader's barrier
+                acc.advance(2);
+            }
+            const int col0 = J * T2 + half * (T2 / 2);
+            float* g = G + (size_t)row + (size_t)col0 * ld;
+#pragma unroll
+            for (int c = 0; c < T2 / 2; c++) {
+                if (row < p && col0 + c < p) g[(size_t)c * ld] = sum[c];
+                sum[c] = 0.f;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                               // no CTA may exit while its partner can still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // upper triangle <- lower triangle (32 x 32 tiles through shared memory, coalesced both ways)
 __global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ G, int p, long long ld)
 {
@@ -415,12 +669,32 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
     if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < 1 || p < 8) return false;
     if (n >= 2147483647LL - BK || p >= 2147483647LL - TN) return false;
     if (col_end < 0) col_end = p;
+    const char* kenv = getenv("B200ADMM_GRAM_KERNEL");          // "1cta": single-CTA kernel; default: CTA-pair kernel
+    const bool pair_kernel = !(kenv && !strcmp(kenv, "1cta")) && exact_hi != 0 && p >= 256 && (sm_count() % 2 == 0);
+    const int nk = (int)((n + BK - 1) / BK);
+    if (pair_kernel) {
+        if (col_begin % T2 != 0 || (col_end % T2 != 0 && col_end != p)) return false;
+        const int I0 = (int)(col_begin / T2), I1 = (int)((col_end + T2 - 1) / T2);
+        int ntiles = 0;
+        for (int i = I0; i < I1; i++) ntiles += i + 1;
+        if (ntiles > 0) {
+            CUtensorMap map;
+            make_map(&map, X, n, ldx, p, 128);
+            static bool attr2 = false;
+            if (!attr2) {
+                CUDA_CHECK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+                attr2 = true;
+            }
+            const int grid = 2 * std::min(ntiles, sm_count() / 2);
+            gram_pair_kernel<<<grid, 512, P2_SMEM, s>>>(map, G, (int)p, (long long)ld, nk, I0, ntiles);
+            KERNEL_CHECK();
+        }
+    } else {
     if (col_begin % TM != 0 || (col_end % TM != 0 && col_end != p)) return false;     // panels are whole row blocks
     const int nJ = (int)((p + TN - 1) / TN);
     const int I0 = (int)(col_begin / TM), I1 = (int)((col_end + TM - 1) / TM);
     int ntiles = 0;
     for (int i = I0; i < I1; i++) ntiles += std::min(nJ, col_blocks_of(i));
-    const int nk = (int)((n + BK - 1) / BK);
     if (ntiles > 0) {
         const int grid = std::min(ntiles, sm_count());
         CUtensorMap mapA, mapB;
@@ -434,6 +708,7 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
         const char* dbg_env = getenv("B200ADMM_GRAM_DBG");     // timing experiments only (results are wrong when set)
         gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, I0, nJ, ntiles, exact_hi ? 1 : 0, dbg_env ? atoi(dbg_env) : 0);
         KERNEL_CHECK();
+    }
     }
     if (mirror) {
         dim3 mg((unsigned)((p + 31) / 32), (unsigned)((p + 31) / 32));

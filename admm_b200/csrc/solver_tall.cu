@@ -170,7 +170,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         const size_t esz = d->dtype == B200ADMM_F64_HOST ? 8 : 4;
         i64 pw = (i64)(((size_t)3 << 30) / ((size_t)n_local * esz));          // ~3 GB of host data per panel
         if (const char* pw_env = getenv("B200ADMM_PANEL_COLS")) pw = atoll(pw_env);     // tests: force several panels
-        pw = std::max<i64>(128, (pw / 128) * 128);
+        pw = std::max<i64>(256, (pw / 256) * 256);                        // whole 256-column row blocks of the pair kernel
         const int npan = (int)((p + pw - 1) / pw);
         DevBuf<float> tmp(2 * pw + 8);
         DevBuf<double> slab[2];
