@@ -305,15 +305,37 @@ void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* k
     DevBuf<T> work(chol_work<T>(p));
     DevBuf<T> tmp((size_t)p * 128);
     DevBuf<int> info(1);
-    chol_lower<T>(s, a, p, ld, work.p, info.p);
+    // The blocked factorisation and inverse are ~7 short launches per 128 columns (550 at p = 1e4), each
+    // far shorter than a host hiccup: they are recorded into a CUDA graph and replayed as ONE launch, so
+    // the device never waits for the host between them.  A non-positive pivot does not stop the kernels
+    // (the pivot is replaced, `info` remembers the column); it is reported after the graph has run.
+    const char* genv = getenv("B200ADMM_GRAPH");
+    const bool use_graph = !(genv && !strcmp(genv, "0"));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    try {
+        chol_lower<T>(s, a, p, ld, work.p, info.p);
+        if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
+        tri_inverse_lower<T>(s, a, p, ld, work.p, W, ld, tmp.p);
+        gram_of_lower<T>(s, W, p, ld, a, ld);
+    } catch (...) {
+        if (use_graph) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); }
+        throw;
+    }
+    if (use_graph) {
+        CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaGraphLaunch(exec, s));
+    }
     int h = 0;
     CUDA_CHECK(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    const cudaError_t sync_rc = cudaStreamSynchronize(s);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    CUDA_CHECK(sync_rc);
     if (info_host) *info_host = h;
     if (h != 0) throw CodeError(B200ADMM_ENOTSPD, "Cholesky factorisation met a non-positive pivot at column " + std::to_string(h));
-    if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
-    tri_inverse_lower<T>(s, a, p, ld, work.p, W, ld, tmp.p);
-    gram_of_lower<T>(s, W, p, ld, a, ld);
 }
 template void spd_inverse<float>(cudaStream_t, float*, i64, i64, float*, int*, float*);
 template void spd_inverse<double>(cudaStream_t, double*, i64, i64, double*, int*, double*);
@@ -534,8 +556,12 @@ int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g, int use_te
         bool done = false;
         if (use_tensor) {
             CUDA_CHECK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)p * (size_t)p, c.stream));
-            done = gram_tn_tensor(c.stream, (const float*)x, n, n, p, (float*)g, p, use_tensor > 1 ? 1 : 0);
+            // use_tensor: 1 = TF32 truncation split, 2 = TF32 round-to-nearest split, 3 = fp16 split (unit-scale data)
+            const int split = use_tensor >= 3 ? GRAM_SPLIT_F16 : (use_tensor == 2 ? GRAM_SPLIT_TF32 : GRAM_SPLIT_TRUNC);
+            done = gram_tn_tensor(c.stream, (const float*)x, n, n, p, (float*)g, p, split);
             if (!done) throw ArgError("tensor-core Gram kernel cannot take this shape (needs n % 4 == 0 and p >= 8)");
+            if (split == GRAM_SPLIT_F16 && gram_f16_overflowed(c.stream))
+                throw ArgError("fp16-split Gram kernel: a value exceeds the fp16 range (use mode 2)");
         }
         if (!done)
             gemm<float>(c.stream, true, false, p, p, n, 1.f, (const float*)x, n, (const float*)x, n, 0.f, (float*)g, p, GEMM_LOWER | GEMM_MIRROR);

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstring>
 #include <cstdlib>
 
@@ -611,6 +612,253 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G,
     }
 }
 
+// =================================================================================================
+// CTA-pair kernel on PRE-SPLIT fp16 operands (tcgen05 kind::f16, twice the TF32 rate, no splitter).
+//
+// For columns of unit scale (DataStd flags 1 and 3: |x| <= sqrt(n), typical |x| ~ 1) an fp16 pair
+// carries the same 22 significant bits as the TF32 pair:  hi = rn_f16(x) (11 bits), lo = rn_f16(x - hi)
+// (|lo| <= 2^-11 |x|; exact to 2^-25 absolute once it is an fp16 subnormal).  Every product hi*hi, lo*hi,
+// hi*lo is exact in the fp32 accumulator exactly as in the TF32 kernel, so the result has the same
+// error bound (dropped lo*lo < 2^-22 |a b|) at twice the tensor rate.
+//
+// The ncu capture of the TF32 pair kernel (profiles/r1b) shows its five splitter warps never idle
+// (a third of their time in the release fence of the cross-CTA arrive) while the tensor pipe is 47 %
+// busy: every element of X was being split again for each of the ~p/256 tiles it takes part in.
+// Here the split is done ONCE by split_f16_blocked_kernel into a tile-blocked operand array: for every
+// 32 rows of a column, 32 hi halves followed by 32 lo halves (the same 128 bytes as the fp32 data).  TMA
+// delivers operand rows of 128 bytes (SWIZZLE_128B) that the tensor core reads directly: bytes 0-63
+// of a row are the hi K-slice, bytes 64-127 the lo K-slice.  Per CTA and 32-row stage: 32 KB of TMA
+// traffic, six M = 256, N = 256, K = 16 instructions, no CUDA-core work outside the epilogue.
+//   warp 0  TMA producer (each CTA loads its own 128 A rows and 128 B rows; both CTAs' loads complete
+//           on the LEADER's full barrier, cp.async.bulk.tensor ... cta_group::2)
+//   warp 1  MMA issuer (leader CTA only)       warp 2  TMEM alloc
+//   warps 4-11  epilogue (128 accumulator registers per thread, chunked fp32 accumulation as above)
+// =================================================================================================
+constexpr int H_STAGES = 7;
+constexpr int H_THREADS = 384;
+constexpr int H_SMEM = H_STAGES * P2_STAGE + 1024 + 256;
+// kind::f16: A, B = F16 (format 0), D = F32; M = 256 (pair), N = 256
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(T2 >> 3) << 17) | ((uint32_t)(T2 >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// TMA load into this CTA's shared memory whose completion is counted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b)      // a -> low half (lower address), b -> high half
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u)
+{
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+// Operand layout ("blocked"): the matrix is cut into boxes of 128 columns x 32 rows; box (cb, kb) is the
+// 16 KB at byte offset (cb * nk + kb) * 16384 and holds, for each of its 128 columns, one 128-byte row:
+// the 32 hi halves followed by the 32 lo halves of rows 32 kb .. 32 kb + 31.  One TMA box = one
+// contiguous 16 KB burst (with column-major X a box was 128 rows of 128 bytes, 4 n bytes apart: at
+// n = 1e6 the ncu capture showed 1.4 TB of DRAM reads at a third of the HBM rate and the tensor pipe
+// 38 % busy; see profiles/r1f).
+// Four threads per (column, k-block) unit: thread t reads rows 8t .. 8t+7 of the unit (32 bytes) and writes
+// 16 bytes of hi at byte 16 t and 16 bytes of lo at byte 64 + 16 t of the unit's row; a warp takes 8
+// consecutive k-blocks of one column (1 KB of contiguous input).  Rows >= n and columns >= p give zeros.
+__global__ void __launch_bounds__(256) split_f16_blocked_kernel(const float* __restrict__ X, long long n, long long ld, long long p,
+                                                                long long nk, long long cb0, long long ncb,
+                                                                unsigned char* __restrict__ Xb, int* __restrict__ overflow)
+{
+    const long long nk8 = (nk + 7) / 8;                              // groups of 8 k-blocks
+    const long long total = ncb * 128 * nk8;                         // warp tasks: (column, group)
+    const int lane = threadIdx.x & 31, t = lane & 3, u = lane >> 2;
+    bool ovf = false;
+    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const long long g = w % nk8, cc = w / nk8;                   // consecutive warps walk down one column
+        const long long cb = cb0 + cc / 128;
+        const int c = (int)(cc % 128);
+        const long long col = cb * 128 + c, kb = g * 8 + u;
+        if (kb >= nk) continue;
+        const long long r0 = kb * 32 + 8 * t;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.f;
+        if (col < p) {
+            const float* src = X + col * ld + r0;
+            if (r0 + 8 <= n) {
+                const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(src)), b = ld_stream_f4(reinterpret_cast<const float4*>(src) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) if (r0 + i < n) v[i] = src[i];
+            }
+        }
+        const float amax = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                                 fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+        ovf |= !(amax <= 65000.f);
+        uint4 h, l;
+        h.x = pack_half2(v[0], v[1]); h.y = pack_half2(v[2], v[3]); h.z = pack_half2(v[4], v[5]); h.w = pack_half2(v[6], v[7]);
+        const float2 f0 = unpack_half2(h.x), f1 = unpack_half2(h.y), f2 = unpack_half2(h.z), f3 = unpack_half2(h.w);
+        l.x = pack_half2(v[0] - f0.x, v[1] - f0.y); l.y = pack_half2(v[2] - f1.x, v[3] - f1.y);
+        l.z = pack_half2(v[4] - f2.x, v[5] - f2.y); l.w = pack_half2(v[6] - f3.x, v[7] - f3.y);
+        unsigned char* row = Xb + ((cb * nk + kb) * 128 + c) * 128;
+        *reinterpret_cast<uint4*>(row + 16 * t) = h;
+        *reinterpret_cast<uint4*>(row + 64 + 16 * t) = l;
+    }
+    if (ovf) atomicExch(overflow, 1);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H_THREADS, 1)
+gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* op = base;                         // H_STAGES x (A | B), rows of 32 hi | 32 lo halves
+    uint64_t* bars = reinterpret_cast<uint64_t*>(op + H_STAGES * P2_STAGE);
+    uint64_t* full = bars;                            // [H_STAGES] leader's: TMA of both CTAs (64 KB) -> MMA
+    uint64_t* empty = bars + H_STAGES;                // [H_STAGES] MMA commit (multicast) -> both TMA producers
+    uint64_t* tmem_full = bars + 2 * H_STAGES;        // [2]        MMA commit (multicast) -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;             // [2]        leader's: epilogue warps of both CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < H_STAGES; i++) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(tmem_full + i), 1); mbar_init(smem_u32(tmem_empty + i), 2 * 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nchunk = (nk + CHUNK_STEPS - 1) / CHUNK_STEPS;
+
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+
+    if (warp == 0) {
+        // ================================ TMA producer (each CTA) =======================
+        if (lane == 0) {
+            Ring r;
+            for (int t = pair; t < ntiles; t += npairs) {
+                int I, J;
+                pair_tile_coords(t, I0, I, J);
+                for (int ks = 0; ks < nk; ks++) {
+                    mbar_wait(smem_u32(empty + r.idx), r.phase ^ 1u);
+                    const uint32_t fb = mapa_rank(smem_u32(full + r.idx), 0);      // the leader's barrier counts both CTAs' bytes
+                    if (rank == 0) mbar_expect_tx(smem_u32(full + r.idx), 2 * P2_STAGE);
+                    const uint32_t dst = smem_u32(op + r.idx * P2_STAGE);
+                    // box (cb, ks) of the blocked operand: rows ((cb * nk + ks) * 128 ...) of a dense [rows][64 halves] array
+                    tma_load_2d_pair(dst, &map, 0, ((2 * I + (int)rank) * nk + ks) * 128, fb);
+                    tma_load_2d_pair(dst + P2_A_BYTES, &map, 0, ((2 * J + (int)rank) * nk + ks) * 128, fb);
+                    r.advance(H_STAGES);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ================
+        if (rank == 0 && lane == 0) {
+            Ring q, acc;
+            for (int t = pair; t < ntiles; t += npairs) {
+                for (int ks = 0; ks < nk; ks++) {
+                    const int c = ks % CHUNK_STEPS;
+                    if (c == 0) {
+                        mbar_wait_cluster(smem_u32(tmem_empty + acc.idx), acc.phase ^ 1u);
+                        tc_fence_after();
+                    }
+                    mbar_wait_cluster(smem_u32(full + q.idx), q.phase);      // both CTAs' operand tiles have landed
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(acc.idx * T2);
+                    const uint32_t oa = smem_u32(op + q.idx * P2_STAGE);
+                    const uint64_t a_hi = umma_desc_k(oa), b_hi = umma_desc_k(oa + P2_A_BYTES);
+                    const uint64_t a_lo = a_hi + (64 >> 4), b_lo = b_hi + (64 >> 4);   // lo halves: bytes 64..127 of each row
+#pragma unroll
+                    for (int sub = 0; sub < 2; sub++) {
+                        const uint64_t off = (uint64_t)(sub * 32 >> 4);                // 16 halves = 32 bytes along K
+                        tc_mma_f16_pair(d, a_hi + off, b_hi + off, IDESC_F16, (c > 0 || sub > 0) ? 1u : 0u);
+                        tc_mma_f16_pair(d, a_lo + off, b_hi + off, IDESC_F16, 1u);
+                        tc_mma_f16_pair(d, a_hi + off, b_lo + off, IDESC_F16, 1u);
+                    }
+                    tc_commit_pair(smem_u32(empty + q.idx));
+                    if (c == CHUNK_STEPS - 1 || ks == nk - 1) {
+                        tc_commit_pair(smem_u32(tmem_full + acc.idx));
+                        acc.advance(2);
+                    }
+                    q.advance(H_STAGES);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue (each CTA: its 128 rows) =============
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;                  // which 128 of the 256 accumulator columns
+        Ring acc;
+        float sum[T2 / 2];
+#pragma unroll
+        for (int c = 0; c < T2 / 2; c++) sum[c] = 0.f;
+        for (int t = pair; t < ntiles; t += npairs) {
+            int I, J;
+            pair_tile_coords(t, I0, I, J);
+            const int row = I * T2 + (int)rank * 128 + quad * 32 + lane;
+            for (int ch = 0; ch < nchunk; ch++) {
+                mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
+                tc_fence_after();
+#pragma unroll
+                for (int cg = 0; cg < T2 / 2 / 32; cg++) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc.idx * T2 + half * (T2 / 2) + cg * 32);
+                    tc_ld32(taddr, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; c++) sum[cg * 32 + c] += __uint_as_float(v[c]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(smem_u32(tmem_empty + acc.idx), 0);   // one arrival per warp on the leader's barrier
+                acc.advance(2);
+            }
+            const int col0 = J * T2 + half * (T2 / 2);
+            float* g = G + (size_t)row + (size_t)col0 * ld;
+#pragma unroll
+            for (int c = 0; c < T2 / 2; c++) {
+                if (row < p && col0 + c < p) g[(size_t)c * ld] = sum[c];
+                sum[c] = 0.f;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // upper triangle <- lower triangle (32 x 32 tiles through shared memory, coalesced both ways)
 __global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ G, int p, long long ld)
 {
@@ -659,17 +907,115 @@ void make_map(CUtensorMap* m, const float* X, i64 n, i64 ldx, i64 p, int box_col
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+// operand view of the blocked array: dense rows of 64 halves (128 bytes), 128 rows per box
+void make_map_h(CUtensorMap* m, const void* Xb, i64 nrows)
+{
+    cuuint64_t gdim[2] = { 64u, (cuuint64_t)nrows };
+    cuuint64_t gstride[1] = { 128u };
+    cuuint32_t box[2] = { 64u, 128u };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(Xb), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (fp16 view) failed with code " + std::to_string((int)r));
+}
+
 }  // namespace
 
+// device flag raised by the fp16 split when a value does not fit the fp16 range
+static int* overflow_flag()
+{
+    static int* flag = nullptr;
+    if (!flag) {
+        CUDA_CHECK(cudaMalloc(&flag, sizeof(int)));
+        CUDA_CHECK(cudaMemset(flag, 0, sizeof(int)));
+    }
+    return flag;
+}
+
+bool gram_f16_overflowed(cudaStream_t s)
+{
+    int h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, overflow_flag(), sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (h) CUDA_CHECK(cudaMemsetAsync(overflow_flag(), 0, sizeof(int), s));
+    return h != 0;
+}
+
+bool gram_f16_usable(i64 n, i64 p)
+{
+    const char* kenv = getenv("B200ADMM_GRAM_KERNEL");          // "tf32" / "1cta": never take the fp16 path
+    const i64 nk = (n + 31) / 32, pb = (p + 127) / 128;
+    return p >= 256 && (sm_count() % 2 == 0) && !kenv && n >= 1 && pb * nk * 128 < 2147483647LL;
+}
+
+size_t gram_f16_blocked_bytes(i64 n, i64 p)
+{
+    const i64 nk = (n + 31) / 32, pb = (p + 127) / 128;
+    return (size_t)pb * (size_t)nk * 16384;
+}
+
+void gram_split_f16_blocked(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i64 col_begin, i64 col_end, void* Xb)
+{
+    if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0) throw ArgError("gram_split_f16_blocked: X must be 16-byte aligned with a leading dimension that is a multiple of 4");
+    if (col_end < 0) col_end = p;
+    if (col_begin % 128 != 0) throw ArgError("gram_split_f16_blocked: panels start at a multiple of 128 columns");
+    if (col_end <= col_begin) return;
+    const long long nk = (n + 31) / 32, cb0 = col_begin / 128, ncb = (col_end + 127) / 128 - cb0;
+    const long long tasks = ncb * 128 * ((nk + 7) / 8);
+    const unsigned grid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)sm_count() * 32);
+    split_f16_blocked_kernel<<<grid, 256, 0, s>>>(X, (long long)n, (long long)ldx, (long long)p, nk, cb0, ncb, (unsigned char*)Xb, overflow_flag());
+    KERNEL_CHECK();
+}
+
+bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G, i64 ld, i64 col_begin, i64 col_end, bool mirror)
+{
+    if ((((uintptr_t)Xb) & 127) != 0 || !gram_f16_usable(n, p)) return false;
+    if (col_end < 0) col_end = p;
+    if (col_begin % T2 != 0 || (col_end % T2 != 0 && col_end != p)) return false;
+    const i64 nk = (n + 31) / 32, pb = (p + 127) / 128;
+    const int I0 = (int)(col_begin / T2), I1 = (int)((col_end + T2 - 1) / T2);
+    int ntiles = 0;
+    for (int i = I0; i < I1; i++) ntiles += i + 1;
+    if (ntiles > 0) {
+        CUtensorMap map;
+        // a pair tile reads column blocks 2 I, 2 I + 1: with an odd number of blocks the last box row is out of
+        // bounds and TMA fills it with zeros
+        make_map_h(&map, Xb, pb * nk * 128);
+        static bool attr = false;
+        if (!attr) {
+            CUDA_CHECK(cudaFuncSetAttribute(gram_pair_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+            attr = true;
+        }
+        const int grid = 2 * std::min(ntiles, sm_count() / 2);
+        gram_pair_h_kernel<<<grid, H_THREADS, H_SMEM, s>>>(map, G, (int)p, (long long)ld, (int)nk, I0, ntiles);
+        KERNEL_CHECK();
+    }
+    if (mirror) {
+        dim3 mg((unsigned)((p + 31) / 32), (unsigned)((p + 31) / 32));
+        mirror_lower_kernel<<<mg, 256, 0, s>>>(G, (int)p, (long long)ld);
+        KERNEL_CHECK();
+    }
+    return true;
+}
+
 // Writes the full symmetric p x p matrix into G (leading dimension ld).
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi,
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int split,
                     i64 col_begin, i64 col_end, bool mirror)
 {
     // 16-byte aligned base and column stride (TMA); rows beyond n are zero-filled by the hardware
     if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < 1 || p < 8) return false;
     if (n >= 2147483647LL - BK || p >= 2147483647LL - TN) return false;
     if (col_end < 0) col_end = p;
-    const char* kenv = getenv("B200ADMM_GRAM_KERNEL");          // "1cta": single-CTA kernel; default: CTA-pair kernel
+    if (split == GRAM_SPLIT_F16 && gram_f16_usable(n, p) && col_begin == 0 && col_end == p) {
+        DevBuf<unsigned char> Xb(gram_f16_blocked_bytes(n, p));
+        gram_split_f16_blocked(s, X, n, ldx, p, 0, p, Xb.p);
+        const bool ok = gram_tn_f16_blocked(s, Xb.p, n, p, G, ld, 0, p, mirror);
+        CUDA_CHECK(cudaStreamSynchronize(s));                   // Xb is released on return
+        if (ok) return true;
+    }
+    const int exact_hi = split != GRAM_SPLIT_TRUNC;
+    const char* kenv = getenv("B200ADMM_GRAM_KERNEL");          // "1cta": single-CTA TF32 kernel
     const bool pair_kernel = !(kenv && !strcmp(kenv, "1cta")) && exact_hi != 0 && p >= 256 && (sm_count() % 2 == 0);
     const int nk = (int)((n + BK - 1) / BK);
     if (pair_kernel) {

@@ -17,15 +17,32 @@ template <class T>
 void gemm(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, i64 K, T alpha, const T* A, i64 lda,
           const T* B, i64 ldb, T beta, T* C, i64 ldc, int mode);
 
-// ---- gram_tc.cu : X'X on the tcgen05 tensor cores (3xTF32 split, fp32-accurate) ------------
+// ---- gram_tc.cu : X'X on the tcgen05 tensor cores (split products, fp32-accurate) ----------
 // G (p x p, leading dimension ld) must be zeroed by the caller; the full symmetric matrix is written.
-// exact_hi = 1 also rewrites the high parts in shared memory (does not rely on the tensor core
-// ignoring the 13 low mantissa bits of its fp32-typed operands).
+// split selects how every fp32 operand is cut into two tensor-core operands (three products per k):
+enum GramSplit {
+    GRAM_SPLIT_TRUNC = 0,   // TF32, hi = the raw word (the tensor core ignores the 13 low mantissa bits)
+    GRAM_SPLIT_TF32  = 1,   // TF32, hi / lo rounded to nearest and rewritten in shared memory (any fp32 data)
+    GRAM_SPLIT_F16   = 2,   // fp16 hi / lo (kind::f16, twice the TF32 rate): data of unit scale only, i.e. columns
+                            // standardised by DataStd; out-of-range values raise a flag -> gram_f16_overflowed()
+};
 // returns false if the shape cannot use the tensor path (caller falls back to gemm<float>)
 // [col_begin, col_end): only the row blocks of G belonging to these columns of X are computed (they need
 // columns 0 .. col_end of X); mirror = false defers the lower -> upper copy to the last panel.
-bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int exact_hi,
+bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int split,
                     i64 col_begin = 0, i64 col_end = -1, bool mirror = true);
+// fp16 path in two steps, for callers that build the Gram matrix panel by panel (the tall solver):
+//   gram_split_f16_blocked : columns [col_begin, col_end) of X (n x p, column-major, ldx % 4 == 0) -> the blocked
+//                            fp16 hi | lo operand array Xb (gram_f16_blocked_bytes(n, p) bytes; 128-column x
+//                            32-row boxes of 16 KB, one TMA burst each); col_begin % 128 == 0
+//   gram_tn_f16_blocked    : same contract as gram_tn_tensor, operands read from Xb (columns < col_end split)
+bool gram_f16_usable(i64 n, i64 p);
+size_t gram_f16_blocked_bytes(i64 n, i64 p);
+void gram_split_f16_blocked(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i64 col_begin, i64 col_end, void* Xb);
+bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G, i64 ld,
+                         i64 col_begin = 0, i64 col_end = -1, bool mirror = true);
+// synchronises `s`; true (and the flag is cleared) if an fp16 split since the last call met |x| > 65000
+bool gram_f16_overflowed(cudaStream_t s);
 
 // ---- gemv.cu -----------------------------------------------------------------------------
 // out[j] = sum_i A(i,j) v[i]   (A m x ncol column-major, lda)  -- one dot product per column

@@ -142,12 +142,19 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     b200admm_timing T;
     memset(&T, 0, sizeof T);
 
+    // B200ADMM_GRAM: "simt" CUDA-core kernel; "trunc" / "tf32" force a TF32 split.  Default: with DataStd flag 3
+    // (centred, unit-norm columns: |x| <= sqrt(n)) the standardised copy is split once into a tile-blocked array
+    // of fp16 hi / lo halves and the Gram kernel runs kind::f16 on it (twice the TF32 rate, same 22-bit operands);
+    // any other flag keeps the TF32 split, whose 8-bit exponent covers every fp32 column scale.
+    const char* gram_env = getenv("B200ADMM_GRAM");
+    const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
+    const int split_mode = (gram_env && !strcmp(gram_env, "trunc")) ? GRAM_SPLIT_TRUNC : GRAM_SPLIT_TF32;
+    const bool use_f16 = want_tensor && !gram_env && flag == 3 && (double)n < 4.0e9 && gram_f16_usable(n_local, p);
     const i64 ldx = (n_local + 3) & ~(i64)3;
     const bool padded = ldx != n_local;
-    const char* gram_env = getenv("B200ADMM_GRAM");            // "simt": CUDA-core kernel; "trunc": truncation split
-    const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
-    const int split_mode = (gram_env && !strcmp(gram_env, "trunc")) ? 0 : 1;
     DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
+    DevBuf<unsigned char> Xb;
+    if (use_f16) Xb.alloc(gram_f16_blocked_bytes(n_local, p));
     DevBuf<float> d_meanX(p), d_scaleX(p);
     DevBuf<float> XY(ld);
     DevBuf<float> G((size_t)p * (size_t)ld);
@@ -204,9 +211,16 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
             }
             standardize_cols_sharded(s, dstp, ldx, dstp, ldx, n_local, n, pc, flag, d_meanX.p + c0, d_scaleX.p + c0, tmp.p);
             gemv_t<float>(s, dstp, n_local, pc, ldx, ys.p, XY.p + c0);
-            if (!gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode, c0, c0 + pc, k == npan - 1))
-                throw CudaError("pipelined Gram: tensor kernel declined the shape");
+            bool ok;
+            if (use_f16) {
+                gram_split_f16_blocked(s, Xs.p, n_local, ldx, p, c0, c0 + pc, Xb.p);
+                ok = gram_tn_f16_blocked(s, Xb.p, n_local, p, G.p, ld, c0, c0 + pc, k == npan - 1);
+            } else {
+                ok = gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode, c0, c0 + pc, k == npan - 1);
+            }
+            if (!ok) throw CudaError("pipelined Gram: tensor kernel declined the shape");
         }
+        if (use_f16 && gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
         fetch_std_stats(s, p, flag, d_meanX.p, d_scaleX.p, st);
         T.gram = tm.stop();                                   // copy + DataStd + X'y + Gram, overlapped
         CUDA_CHECK(cudaStreamSynchronize(cs));
@@ -246,7 +260,15 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, XY.p);
     allreduce_sum(s, XY.p, p);
     G.zero(s);
-    const bool on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode);
+    bool on_tensor = false;
+    if (use_f16) {
+        gram_split_f16_blocked(s, Xs.p, n_local, ldx, p, 0, p, Xb.p);
+        on_tensor = gram_tn_f16_blocked(s, Xb.p, n_local, p, G.p, ld);
+        if (!on_tensor) throw CudaError("fp16 Gram kernel declined the shape");
+        if (gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
+    } else {
+        on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode);
+    }
     if (!on_tensor) {
         // CUDA-core path (shapes the tensor kernel does not take)
         gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
@@ -258,6 +280,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), XY.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     Xs.release();                                       // the tall solver never touches X again
+    Xb.release();
     ys.release();
 
     float lambda0 = 0.f;

@@ -61,7 +61,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (the recipe's clocks line)."""
+    """SM clock / throttle reasons during the timed region (the recipe's clocks line).  Sampled through NVML
+    in-process (nvidia_ml_py); spawning nvidia-smi five times a second costs ~0.2-0.7 s of driver
+    initialisation per call on an 8-GPU node and was seen to stall the timed CUDA calls themselves.
+    nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -72,7 +75,45 @@ class ClockSampler:
         self.stop_flag = threading.Event()
         self.th = None
 
+    def _nvml_handle(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ent = vis.split(",")[self.index].strip()
+                if ent.isdigit():
+                    phys = int(ent)
+                else:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(ent.encode() if hasattr(ent, "encode") else ent)
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            return None, None
+
+    def _run_nvml(self, nv, h):
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
     def _run(self):
+        nv, h = self._nvml_handle()
+        if nv is not None and h is not None:
+            self.source = "nvml"
+            return self._run_nvml(nv, h)
+        self.source = "nvidia-smi"
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -101,7 +142,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": getattr(self, "source", None)}
 
 
 def host_threads():
@@ -322,6 +363,7 @@ def main():
                            "path_wall_s": e_wall / args.e2e_steps, "steps": args.e2e_steps,
                            "device_s_per_step": e_dev / args.e2e_steps,
                            "phase_s": {k: float(np.mean([f.info["timing"][k] for f in fh])) for k in fh[-1].info["timing"]},
+                           "phase_s_per_step": [{k: round(float(v), 4) for k, v in f.info["timing"].items()} for f in fh],
                            "input": "float32 column-major, pinned host memory"}
             del Xh, yh
         except Exception as ex:  # pinned allocation can fail on small hosts: say so, do not fake a number

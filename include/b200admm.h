@@ -171,7 +171,9 @@ int b200admm_synth_f32(void* x_dev, void* y_dev, int64_t nrows, int64_t p, int64
 int b200admm_k_standardize_f32(const void* x_in, void* x_out, void* y_inout, int64_t n, int64_t p,
                                int standardize, int intercept,
                                float* meanx_host, float* scalex_host, float* meany_scaley_host);
-/* use_tensor: 0 CUDA cores, 1 tcgen05 3xTF32 with truncation split (raw tile serves as hi), 2 the same with a round-to-nearest split (default of the solvers) */
+/* use_tensor: 0 CUDA cores, 1 tcgen05 3xTF32 with truncation split (raw tile serves as hi), 2 the same with a
+ * round-to-nearest split (any fp32 data), 3 tcgen05 3xFP16 hi/lo split (unit-scale columns only, i.e. data
+ * standardised by DataStd -- what the solvers use there; values beyond the fp16 range are an error here) */
 int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g /* p x p, full */, int use_tensor);
 int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v, void* out);
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host);                 /* lower, in place */

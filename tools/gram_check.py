@@ -21,8 +21,8 @@ if n * p <= 2_000_000_000:
     ref = X64 @ X64.t()
     del X64
     dscale = torch.sqrt(torch.outer(torch.diag(ref), torch.diag(ref)))
-MODES = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2]
-for mode, name in ((0, "cuda-core fp32"), (1, "tcgen05 3xTF32 (trunc split)"), (2, "tcgen05 3xTF32 (rn split)")):
+MODES = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3]
+for mode, name in ((0, "cuda-core fp32"), (1, "tcgen05 3xTF32 (trunc split)"), (2, "tcgen05 3xTF32 (rn split)"), (3, "tcgen05 3xFP16 (rn split)")):
     if mode not in MODES:
         continue
     G = torch.zeros((p, p), dtype=torch.float32, device="cuda")
