@@ -20,7 +20,7 @@ EXPORTS = [
     "b200admm_lasso", "b200admm_enet", "b200admm_parlasso", "b200admm_free_path",
     "b200admm_lad", "b200admm_free_dense", "b200admm_bp",
     "b200admm_comm_id", "b200admm_comm_init", "b200admm_comm_destroy",
-    "b200admm_last_error", "b200admm_version", "b200admm_launch_count", "b200admm_stream", "b200admm_release_cache", "b200admm_device_info", "b200admm_set_trace",
+    "b200admm_last_error", "b200admm_version", "b200admm_launch_count", "b200admm_last_gram_seconds", "b200admm_stream", "b200admm_release_cache", "b200admm_device_info", "b200admm_set_trace",
     "b200admm_synth_f32",
     "b200admm_k_standardize_f32", "b200admm_k_gram_f32", "b200admm_k_gemv_t_f32",
     "b200admm_k_chol_f32", "b200admm_k_spd_inverse_f32", "b200admm_k_fused_zu_f32",
@@ -73,6 +73,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.b200admm_last_error.restype = C.c_char_p
         L.b200admm_launch_count.restype = C.c_ulonglong
+        L.b200admm_last_gram_seconds.restype = C.c_double
         L.b200admm_stream.restype = C.c_void_p
         L.b200admm_release_cache.restype = None
         L.b200admm_lasso.argtypes = [C.POINTER(Data), C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,

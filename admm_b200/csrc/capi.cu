@@ -23,6 +23,7 @@ namespace b200 {
 
 static thread_local std::string g_last_error;
 unsigned long long g_launch_count = 0;
+double g_last_gram_seconds = 0.0;
 
 int sm_count()
 {
@@ -59,12 +60,18 @@ Context& ctx()
     return c;
 }
 
-// ---- exact-size recycling of large device blocks ---------------------------------------------
+// ---- exact-size recycling of device blocks ---------------------------------------------------
+// Every solver call allocates the same set of sizes; cudaMalloc / cudaFree are driver calls that take
+// global locks (and cudaFree synchronises the device), ~0.1 s per fit for the 40 GB working copies and a
+// source of multi-millisecond stalls on a busy host even for small blocks.  Freed blocks are therefore
+// kept and handed out again on an exact size match.  All work is ordered on the library's one stream
+// (the copy stream is joined before its buffers are released), so reuse without a synchronisation is safe.
 namespace {
 struct CachedBlock { void* p; size_t bytes; };
 std::vector<CachedBlock>& block_cache() { static std::vector<CachedBlock> c; return c; }
 std::mutex& cache_mutex() { static std::mutex m; return m; }
-constexpr size_t CACHE_MIN_BYTES = (size_t)64 << 20;
+constexpr size_t LARGE_BYTES = (size_t)64 << 20;
+constexpr size_t MAX_LARGE = 16, MAX_SMALL = 256;
 bool cache_enabled()
 {
     static int on = -1;
@@ -82,10 +89,10 @@ void dev_cache_release()
 
 void* dev_alloc(size_t bytes)
 {
-    if (bytes >= CACHE_MIN_BYTES && cache_enabled()) {
+    if (cache_enabled()) {
         std::lock_guard<std::mutex> g(cache_mutex());
         auto& c = block_cache();
-        for (size_t i = 0; i < c.size(); i++)
+        for (size_t i = c.size(); i-- > 0;)
             if (c[i].bytes == bytes) { void* p = c[i].p; c.erase(c.begin() + i); return p; }
     }
     void* p = nullptr;
@@ -105,10 +112,13 @@ void* dev_alloc(size_t bytes)
 void dev_free(void* p, size_t bytes)
 {
     if (!p) return;
-    if (bytes >= CACHE_MIN_BYTES && cache_enabled()) {
+    if (cache_enabled()) {
         std::lock_guard<std::mutex> g(cache_mutex());
         auto& c = block_cache();
-        if (c.size() < 16) { c.push_back({p, bytes}); return; }
+        size_t nlarge = 0;
+        for (auto& b : c) nlarge += b.bytes >= LARGE_BYTES;
+        const bool large = bytes >= LARGE_BYTES;
+        if (large ? nlarge < MAX_LARGE : c.size() - nlarge < MAX_SMALL) { c.push_back({p, bytes}); return; }
     }
     cudaFree(p);
 }
@@ -302,38 +312,56 @@ float coarse_eig_device(cudaStream_t s, const float* S, i64 n, i64 lds, int* nma
 template <class T>
 void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* keep_factor)
 {
-    DevBuf<T> work(chol_work<T>(p));
-    DevBuf<T> tmp((size_t)p * 128);
-    DevBuf<int> info(1);
     // The blocked factorisation and inverse are ~7 short launches per 128 columns (550 at p = 1e4), each
     // far shorter than a host hiccup: they are recorded into a CUDA graph and replayed as ONE launch, so
-    // the device never waits for the host between them.  A non-positive pivot does not stop the kernels
-    // (the pivot is replaced, `info` remembers the column); it is reported after the graph has run.
+    // the device never waits for the host between them.  The instantiated graph (with its workspace) is
+    // kept and replayed as long as the next call brings the same matrices (the block cache hands the same
+    // pointers out again), which also removes the capture cost from every call but the first.  A
+    // non-positive pivot does not stop the kernels (the pivot is replaced, `info` remembers the column);
+    // it is reported after the graph has run.
+    struct FactorGraph {
+        cudaGraphExec_t exec = nullptr;
+        const void *a = nullptr, *W = nullptr, *keep = nullptr;
+        i64 p = -1, ld = -1;
+        unsigned long long kernels = 0;       // kernel nodes in the graph (added to the launch count on every replay)
+        DevBuf<T> work, tmp;
+        DevBuf<int> info;
+    };
+    static FactorGraph& fg = *new FactorGraph;      // lives until process exit (its buffers go back to the driver with the context)
     const char* genv = getenv("B200ADMM_GRAPH");
     const bool use_graph = !(genv && !strcmp(genv, "0"));
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-    try {
-        chol_lower<T>(s, a, p, ld, work.p, info.p);
-        if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
-        tri_inverse_lower<T>(s, a, p, ld, work.p, W, ld, tmp.p);
-        gram_of_lower<T>(s, W, p, ld, a, ld);
-    } catch (...) {
-        if (use_graph) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); }
-        throw;
+    const bool hit = use_graph && fg.exec && fg.a == a && fg.W == W && fg.keep == keep_factor && fg.p == p && fg.ld == ld;
+    if (!hit) {
+        if (fg.exec) { cudaGraphExecDestroy(fg.exec); fg.exec = nullptr; }
+        if (fg.p != p) { fg.work.alloc(chol_work<T>(p)); fg.tmp.alloc((size_t)p * 128); }
+        if (!fg.info.p) fg.info.alloc(1);
+        fg.a = a; fg.W = W; fg.keep = keep_factor; fg.p = p; fg.ld = ld;
+        cudaGraph_t graph = nullptr;
+        const unsigned long long count0 = g_launch_count;
+        if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        try {
+            chol_lower<T>(s, a, p, ld, fg.work.p, fg.info.p);
+            if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
+            tri_inverse_lower<T>(s, a, p, ld, fg.work.p, W, ld, fg.tmp.p);
+            gram_of_lower<T>(s, W, p, ld, a, ld);
+        } catch (...) {
+            if (use_graph) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); }
+            fg.p = -1;
+            throw;
+        }
+        if (use_graph) {
+            CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+            const cudaError_t irc = cudaGraphInstantiate(&fg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (irc != cudaSuccess) { fg.exec = nullptr; fg.p = -1; CUDA_CHECK(irc); }
+            fg.kernels = g_launch_count - count0;
+            g_launch_count = count0;          // counted when the graph actually runs
+        }
     }
-    if (use_graph) {
-        CUDA_CHECK(cudaStreamEndCapture(s, &graph));
-        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
-        CUDA_CHECK(cudaGraphLaunch(exec, s));
-    }
+    if (use_graph) { CUDA_CHECK(cudaGraphLaunch(fg.exec, s)); g_launch_count += fg.kernels; }
     int h = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    const cudaError_t sync_rc = cudaStreamSynchronize(s);
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
-    CUDA_CHECK(sync_rc);
+    CUDA_CHECK(cudaMemcpyAsync(&h, fg.info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
     if (info_host) *info_host = h;
     if (h != 0) throw CodeError(B200ADMM_ENOTSPD, "Cholesky factorisation met a non-positive pivot at column " + std::to_string(h));
 }
@@ -391,6 +419,7 @@ extern "C" {
 const char* b200admm_last_error(void) { return g_last_error.c_str(); }
 int b200admm_version(void) { return B200ADMM_VERSION; }
 unsigned long long b200admm_launch_count(void) { return g_launch_count; }
+double b200admm_last_gram_seconds(void) { return b200::g_last_gram_seconds; }
 void b200admm_release_cache(void) { dev_cache_release(); }
 void* b200admm_stream(void)
 {

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <string>
 #include <stdexcept>
+#include <utility>
+#include <vector>
 
 namespace b200 {
 
@@ -31,6 +33,7 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
     }
 }
 #define CUDA_CHECK(x) ::b200::cuda_check((x), #x, __FILE__, __LINE__)
+extern double g_last_gram_seconds;             // device time of the last tall solver's Gram kernel launches
 extern unsigned long long g_launch_count;       // kernels launched by this library (capi.cu)
 #define KERNEL_CHECK() do { ++::b200::g_launch_count; ::b200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); } while (0)
 
@@ -80,6 +83,33 @@ struct EventTimer {                 // CUDA-event stopwatch on one stream
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
         return ms * 1e-3;
+    }
+};
+
+struct SpanTimer {                  // sums the device time of several bracketed spans; no synchronisation until total()
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    cudaStream_t s;
+    explicit SpanTimer(cudaStream_t s_) : s(s_) {}
+    ~SpanTimer() { for (auto& e : spans) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
+    void begin()
+    {
+        cudaEvent_t a, b;
+        CUDA_CHECK(cudaEventCreate(&a));
+        CUDA_CHECK(cudaEventCreate(&b));
+        spans.push_back({a, b});
+        CUDA_CHECK(cudaEventRecord(a, s));
+    }
+    void end() { CUDA_CHECK(cudaEventRecord(spans.back().second, s)); }
+    double total()   // seconds; every span must have completed (call after a stream synchronisation)
+    {
+        double sum = 0;
+        for (auto& e : spans) {
+            float ms = 0;
+            CUDA_CHECK(cudaEventSynchronize(e.second));
+            CUDA_CHECK(cudaEventElapsedTime(&ms, e.first, e.second));
+            sum += ms * 1e-3;
+        }
+        return sum;
     }
 };
 

@@ -139,6 +139,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     const int flag = (rq.standardize ? 1 : 0) + (rq.intercept ? 2 : 0);
     const i64 ld = (p + 3) & ~(i64)3;
     EventTimer tm(s);
+    SpanTimer gram_kernel_time(s);
     b200admm_timing T;
     memset(&T, 0, sizeof T);
 
@@ -214,10 +215,13 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
             bool ok;
             if (use_f16) {
                 gram_split_f16_blocked(s, Xs.p, n_local, ldx, p, c0, c0 + pc, Xb.p);
+                gram_kernel_time.begin();
                 ok = gram_tn_f16_blocked(s, Xb.p, n_local, p, G.p, ld, c0, c0 + pc, k == npan - 1);
             } else {
+                gram_kernel_time.begin();
                 ok = gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode, c0, c0 + pc, k == npan - 1);
             }
+            gram_kernel_time.end();
             if (!ok) throw CudaError("pipelined Gram: tensor kernel declined the shape");
         }
         if (use_f16 && gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
@@ -263,15 +267,17 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     bool on_tensor = false;
     if (use_f16) {
         gram_split_f16_blocked(s, Xs.p, n_local, ldx, p, 0, p, Xb.p);
+        gram_kernel_time.begin();
         on_tensor = gram_tn_f16_blocked(s, Xb.p, n_local, p, G.p, ld);
+        gram_kernel_time.end();
         if (!on_tensor) throw CudaError("fp16 Gram kernel declined the shape");
         if (gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
     } else {
+        gram_kernel_time.begin();
         on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode);
-    }
-    if (!on_tensor) {
-        // CUDA-core path (shapes the tensor kernel does not take)
-        gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
+        if (!on_tensor)     // CUDA-core path (shapes the tensor kernel does not take)
+            gemm<float>(s, true, false, p, p, n_local, 1.f, Xs.p, ldx, Xs.p, ldx, 0.f, G.p, ld, GEMM_LOWER | GEMM_MIRROR);
+        gram_kernel_time.end();
     }
     allreduce_sum(s, G.p, (size_t)p * (size_t)ld);
     T.gram = tm.stop();
@@ -279,6 +285,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     std::vector<float> h_xy(p);
     CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), XY.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
+    g_last_gram_seconds = gram_kernel_time.total();
     Xs.release();                                       // the tall solver never touches X again
     Xb.release();
     ys.release();

@@ -53,11 +53,25 @@ def parse():
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source).  The tensor-bound kernel is timed inside a long step,
+    so the sustained bf16 figure is its denominator (B200_PROFILING.md)."""
     f = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(f):
         d = json.load(open(f))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1350.0))), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1350.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, n, p):
+    """dram__bytes_read + write of one launch from the committed `ncu --set full` capture (profiles/traffic.json),
+    or None when no capture of this kernel at this size is on file."""
+    try:
+        for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
+            if e["kernel"] == kernel and e["n"] == n and e["p"] == p:
+                return e
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -160,10 +174,38 @@ def algorithmic_bytes_per_iter(p):
 # -------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restated reference) on a bounded sample of the same workload
 # -------------------------------------------------------------------------------------------------
+def wishart_problem(n, p, seed):
+    """(lower(X'X), X'y, lambda grid) of the standardised full-size problem WITHOUT forming X: for i.i.d. Gaussian
+    columns the standardised Gram matrix is n on the diagonal and sqrt(n) N(0,1) off it (central limit of n = 1e6
+    products), and X'y = (G 2 beta* + sqrt(n) N(0,1)) / sd(y) for y = X beta* + noise with X ~ N(0, 2^2).  The CPU
+    iteration count on it is that of the real design (1063 +- a few at n = 1e6, p = 1e4), which a Gram matrix
+    computed from a 20 000-row sample is not: its spectrum is far wider (p / n = 0.5 instead of 0.01)."""
+    rng = np.random.default_rng(seed + 1)
+    G = np.empty((p, p), dtype=np.float32, order="F")
+    rt = np.float32(np.sqrt(n))
+    for j0 in range(0, p, 1024):
+        G[:, j0:j0 + 1024] = rng.standard_normal((p, min(1024, p - j0)), dtype=np.float32) * rt
+    G[np.diag_indices(p)] = np.float32(n)                    # only the lower triangle is read
+    m = min(100, p)
+    b2 = np.zeros(p, dtype=np.float32)
+    b2[:m] = 2.0 * rng.uniform(size=m)
+    sdy = float(np.sqrt(1.0 + float((b2.astype(np.float64) ** 2).sum())))
+    Gb = np.zeros(p, dtype=np.float64)
+    L = np.tril(G[:, :m].astype(np.float64), -1)             # G b over the first m columns, symmetric completion
+    Gb += L @ b2[:m].astype(np.float64)
+    Gb[:m] += np.tril(G[:m, :m].astype(np.float64), -1).T @ b2[:m].astype(np.float64) + float(n) * b2[:m]
+    xy = ((Gb + np.sqrt(n) * rng.standard_normal(p)) / sdy).astype(np.float32)
+    return G, xy
+
+
 def cpu_sample(args, niter_total=None):
     """Times the CPU path piecewise and extrapolates to the full configuration:
-    Gram on `cpu_rows` rows at full p (linear in n), Cholesky + Lanczos at full p, iterations on
-    the first `cpu_lambdas` lambdas of the path (per-iteration cost depends only on p)."""
+    DataStd + Gram on `cpu_rows` rows at full p (linear in n); then Lanczos + Cholesky and the ADMM
+    iterations at full p.  GPU arm (niter_total given): iterations timed on the first `cpu_lambdas`
+    lambdas of the sample's own Gram matrix and the per-iteration cost (which depends only on p) scaled
+    to the GPU run's iteration count.  Reference arm (niter_total None): the whole 100-lambda path is run
+    on a Gram matrix with the full-size problem's statistics (wishart_problem), so its iteration count
+    and iteration seconds are measured, not scaled."""
     from oracle import pyoracle as O
     cores = host_threads()
     bt = O.use_openblas(cores)
@@ -184,11 +226,17 @@ def cpu_sample(args, niter_total=None):
     G = O.gram_tn_f32(x)
     xy = (x.T @ y).astype(np.float32)
     t_gram = time.perf_counter() - t0
-    # scale the sample Gram to the full problem's magnitude so rho / conditioning are comparable
-    G *= np.float32(n / ns)
-    xy *= np.float32(n / ns)
+    full_path = niter_total is None
+    if full_path:
+        del G, xy
+        G, xy = wishart_problem(n, p, args.seed)
+        ncpu_l = nl
+    else:
+        # scale the sample Gram to the full problem's magnitude so rho / conditioning are comparable
+        G *= np.float32(n / ns)
+        xy *= np.float32(n / ns)
+        ncpu_l = max(2, min(args.cpu_lambdas, nl))
     lam0 = float(np.abs(xy).max())
-    ncpu_l = max(2, min(args.cpu_lambdas, nl))
     grid = np.exp(np.linspace(np.log(lam0), np.log(lam0 * 1e-4), nl))[:ncpu_l]
     t0 = time.perf_counter()
     r = O.tall_path_from_gram(G, xy, grid)
@@ -199,14 +247,17 @@ def cpu_sample(args, niter_total=None):
     per_iter = t_iter / max(it_sample, 1)
     full_gram = t_gram * (n / ns)
     full_std = t_std * (n / ns)
-    nit = niter_total if niter_total else int(round(it_sample * nl / ncpu_l))
+    nit = it_sample if full_path else niter_total
     full_wall = full_std + full_gram + t_setup + per_iter * nit
     return {
         "value": nit / full_wall, "unit": "ADMM iters/s (whole lambda path incl. setup)", "cores": cores,
         "kind": "port",
         "sample": ("oracle (restated reference, OpenBLAS %d threads): DataStd+Gram timed on %d of %d rows at p=%d and scaled "
-                   "linearly in n; Lanczos+Cholesky at full p; iterations timed on the first %d of %d lambdas (%d iterations, "
-                   "%.2f ms/iter) and scaled to %d iterations" % (bt, ns, n, p, ncpu_l, nl, it_sample, per_iter * 1e3, nit)),
+                   "linearly in n; Lanczos+Cholesky at full p; " % (bt, ns, n, p)) +
+                  (("all %d lambdas run on a Gram matrix with the full-size design's statistics: %d iterations measured, "
+                    "%.2f ms/iter" % (nl, it_sample, per_iter * 1e3)) if full_path else
+                   ("iterations timed on the first %d of %d lambdas (%d iterations, %.2f ms/iter) and scaled to the GPU run's "
+                    "%d iterations" % (ncpu_l, nl, it_sample, per_iter * 1e3, nit))),
         "path_wall_s_extrapolated": full_wall, "iters_per_s_steady": 1.0 / per_iter,
         "measured_s": {"standardize": t_std, "gram": t_gram, "lanczos_cholesky": t_setup, "iterations": t_iter},
     }
@@ -313,10 +364,17 @@ def main():
     niter_path = int(fits[-1].niter.sum())
     total_iters = sum(int(f.niter.sum()) for f in fits)
     T = {k: float(np.mean([f.info["timing"][k] for f in fits])) for k in fits[-1].info["timing"]}
-    hbm_peak, peak_src = peaks()
+    hbm_peak, tensor_peak, peak_src = peaks()
     bpi = algorithmic_bytes_per_iter(p)
     achieved = bpi * niter_path / T["iterate"] / 1e9
     gram_flops = float(n) * p * (p + 1)
+    gram_kernel_s = float(L.b200admm_last_gram_seconds())         # last timed step, this rank's row block
+    gram_alg_tflops = float(n_local) * p * (p + 1) / max(gram_kernel_s, 1e-9) / 1e12
+    # executed tensor flops: three fp16 products per element, 256 x 256 tiles on and below the diagonal
+    nb = (p + 255) // 256
+    gram_exec_tflops = 3.0 * 2.0 * n_local * 65536.0 * (nb * (nb + 1) // 2) / max(gram_kernel_s, 1e-9) / 1e12
+    tr_gram = ncu_traffic("gram_pair_h_kernel", n_local, p)
+    tr_iter = ncu_traffic("tall_path_kernel", n, p)
 
     line = {
         "metric": "admm_iters_per_sec_full_lambda_path", "value": total_iters / dev_s,
@@ -330,16 +388,25 @@ def main():
         "path_wall_s": dev_s / args.steps, "host_wall_s_per_step": wall_s / args.steps,
         "niter_path": niter_path, "iters_per_sec_steady": niter_path / T["iterate"],
         "phase_s": T,
-        "roofline": {"kernel": "tall_path_kernel (persistent lambda-path iteration kernel)", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     # dram__bytes_read + write of this kernel from the committed ncu --set full capture
-                     # (profiles/r1a_tall_path_kernel_ncu_raw.csv: 343.68 GB for a 1064-iteration launch = 323.0 MB
-                     # per iteration, below the 400.7 MB algorithmic figure because the alternating sweep
-                     # direction leaves the tail of K^-1 in L2), scaled to this launch's iteration count
-                     "traffic": (323.0e6 * niter_path) if (p == 10000) else None, "traffic_unit": "bytes per launch (one launch = the whole lambda path)",
-                     "peak_source": peak_src,
-                     "bytes_per_iteration": bpi, "us_per_iteration": T["iterate"] / max(niter_path, 1) * 1e6},
-        "setup_flops": {"gram_syrk_flop": gram_flops, "gram_tflops": gram_flops / world / max(T["gram"], 1e-9) / 1e12},
+        # the dominant kernel of the step (60 % of the device time): the Gram matrix on the tensor cores.
+        # achieved = ALGORITHMIC flops n p (p + 1) (a symmetric rank-n update) per launch / kernel time; the kernel
+        # executes 3.2x that (three fp16 products per element for fp32 accuracy, whole 256 x 256 tiles on the
+        # diagonal), which `executed` states next to it.
+        "roofline": {"kernel": "gram_pair_h_kernel (tcgen05 kind::f16 CTA-pair Gram, 3-product fp16 split)", "bound": "tensor",
+                     "achieved": gram_alg_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": gram_alg_tflops / tensor_peak,
+                     "traffic": (tr_gram["dram_bytes"] if tr_gram else None), "traffic_source": (tr_gram["source"] if tr_gram else None),
+                     "peak_source": peak_src + ", dense bf16 sustained", "kernel_s": gram_kernel_s,
+                     "algorithmic_flop": float(n_local) * p * (p + 1), "executed": gram_exec_tflops, "executed_frac": gram_exec_tflops / tensor_peak},
+        # the per-iteration hot path named by BASELINE.json: one persistent launch for the whole lambda path
+        "roofline_iteration": {"kernel": "tall_path_kernel (persistent lambda-path iteration kernel)", "bound": "hbm",
+                               "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                               # DRAM bytes per iteration from the ncu capture (below the algorithmic figure: the
+                               # alternating sweep direction leaves the tail of K^-1 in L2), scaled to this launch
+                               "traffic": (tr_iter["dram_bytes_per_iteration"] * niter_path if tr_iter else None),
+                               "traffic_source": (tr_iter["source"] if tr_iter else None),
+                               "traffic_unit": "bytes per launch (one launch = the whole lambda path)", "peak_source": peak_src,
+                               "bytes_per_iteration": bpi, "us_per_iteration": T["iterate"] / max(niter_path, 1) * 1e6},
+        "setup_flops": {"gram_syrk_flop": gram_flops, "gram_phase_tflops": gram_flops / world / max(T["gram"], 1e-9) / 1e12},
         "clocks": clocks, "gpu_launches": int(launches), "device": info["name"],
     }
 

@@ -144,6 +144,10 @@ const char* b200admm_last_error(void);
 int  b200admm_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long b200admm_launch_count(void);
+/* device seconds the Gram-matrix kernel(s) of the most recent lasso / enet call took (CUDA events around
+ * the tensor-core launches only; the `gram` field of b200admm_timing also covers X'y, the operand split
+ * and, for host input, the overlapped copy).  bench.py's tensor roofline is computed from it. */
+double b200admm_last_gram_seconds(void);
 /* the cudaStream_t every kernel of this library is launched on (for event timing by the host
  * program); NULL if no device is usable */
 void* b200admm_stream(void);
