@@ -198,6 +198,41 @@ def test_gram_tensor_cores(K, torch, n, p, mode):
     assert (np.abs(got - ref) / scale).max() < 3e-6 * max(1.0, np.sqrt(n / 1000.0))
 
 
+def test_gram_fp16_split_flags_out_of_range_values(K, torch):
+    """The fp16 hi / lo split is only valid for unit-scale data: a value beyond the fp16 range must be
+    reported, not silently turned into inf (the solvers use this split only behind DataStd flag 3, where
+    |x| <= sqrt(n) holds by construction)."""
+    from admm_b200 import B200AdmmError
+    n, p = 4096, 256
+    x = torch.randn((p, n), device="cuda", dtype=torch.float32)
+    x[3, 100] = 1.0e5
+    g = torch.zeros((p, p), device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    with pytest.raises(B200AdmmError):
+        K.check(K.lib().b200admm_k_gram_f32(x.data_ptr(), n, p, g.data_ptr(), 3))
+    # the flag is cleared by the failed call: the next clean call succeeds, and TF32 takes the same data
+    x[3, 100] = 1.0
+    K.check(K.lib().b200admm_k_gram_f32(x.data_ptr(), n, p, g.data_ptr(), 3))
+    x[3, 100] = 1.0e5
+    K.check(K.lib().b200admm_k_gram_f32(x.data_ptr(), n, p, g.data_ptr(), 2))
+    ref = x.double() @ x.double().t()
+    assert ((g.double() - ref).abs() / torch.sqrt(torch.outer(torch.diag(ref), torch.diag(ref)))).max() < 3e-6
+
+
+def test_gram_fp16_split_small_magnitudes(K, torch):
+    """Columns of very different magnitude inside the unit-scale envelope: the lo half turns subnormal
+    (absolute precision 2^-25) and the result must still match float64 at float32 level on the unit scale."""
+    n, p = 8192, 384
+    g0 = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((p, n), device="cuda", dtype=torch.float32, generator=g0)
+    x[::3] *= 1e-3                                                       # every third column is tiny
+    g = torch.zeros((p, p), device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_gram_f32(x.data_ptr(), n, p, g.data_ptr(), 3))
+    ref = x.double() @ x.double().t()
+    assert (g.double() - ref).abs().max() < 3e-6 * n                     # absolute, relative to unit-scale entries ~ n
+
+
 def test_gram_tensor_rejects_unaligned(K, torch):
     from admm_b200 import B200AdmmError
     x = torch.zeros((64, 1001), device="cuda", dtype=torch.float32)     # n = 1001 is not a multiple of 4

@@ -187,6 +187,30 @@ def test_pipelined_host_ingest_is_bit_identical(A, monkeypatch):
     assert np.array_equal(a.beta.toarray(), b.beta.toarray())
 
 
+def test_fp16_and_tf32_gram_paths_agree(A, O, monkeypatch):
+    """DataStd flag 3 with p >= 256 builds the Gram matrix from pre-split fp16 operands; B200ADMM_GRAM=tf32
+    forces the TF32 split.  Both are float32-accurate, so the fits agree within the stopping tolerance and
+    both match the oracle; without scaling (standardize = FALSE) the TF32 kernel is used whatever the data."""
+    x, y = make_problem(5000, 384, seed=17, nsig=12, mean=0.7)
+    lam = [0.3, 0.05, 0.01]
+    f16 = A.admm_lasso(x, y).penalty(lam).fit()
+    monkeypatch.setenv("B200ADMM_GRAM", "tf32")
+    f32 = A.admm_lasso(x, y).penalty(lam).fit()
+    monkeypatch.delenv("B200ADMM_GRAM")
+    o = O.lasso_path(x, y, lam)
+    tol = max(2e-4, 2.0 * np.sqrt(384) * 1e-5)
+    for k in range(len(lam)):
+        assert_beta_close(dense(f16.beta)[:, k], o["beta"][:, k], tol=tol, band=tol)
+        assert_beta_close(dense(f32.beta)[:, k], o["beta"][:, k], tol=tol, band=tol)
+        assert_beta_close(dense(f16.beta)[:, k], dense(f32.beta)[:, k], tol=tol, band=tol)
+    assert abs(f16.info["rho"] - f32.info["rho"]) < 1e-5 * f32.info["rho"]
+    # any other DataStd flag keeps the TF32 split (here flag 1: scaled, not centred; CTA-pair TF32 kernel at p >= 256)
+    g = A.admm_lasso(x, y, intercept=False).penalty(lam).fit()
+    og = O.lasso_path(x, y, lam, intercept=False)
+    for k in range(len(lam)):
+        assert_beta_close(dense(g.beta)[:, k], og["beta"][:, k], tol=tol, band=tol)
+
+
 def test_user_rho_and_nonconvergence(A, O):
     x, y = make_problem(600, 30, seed=9)
     f = A.admm_lasso(x, y).penalty([0.1]).opts(maxit=3, rho=50.0).fit()
