@@ -723,8 +723,134 @@ __global__ void __launch_bounds__(256) split_f16_blocked_kernel(const float* __r
     if (ovf) atomicExch(overflow, 1);
 }
 
+// DataStd's apply step, X'y and the operand split in ONE pass over the raw columns (flag 3):
+//   x_std = (x - mean_j) * inv_j          exactly col_apply_kernel's arithmetic (stdize.cu), never stored as fp32
+//   partial[j][g] = sum over the 256 rows of group g of x_std * y      (fixed order; xty_reduce_kernel adds the groups)
+//   Xb            = fp16 hi | lo of x_std in the blocked layout above
+// Replaces three passes (apply: read + write, gemv: read, split: read + write) by one read + one write.
+__global__ void __launch_bounds__(256) std_split_xty_kernel(const float* __restrict__ X, long long n, long long ld, long long p,
+                                                            long long nk, long long cb0, long long ncb,
+                                                            const float* __restrict__ mean, const float* __restrict__ inv,
+                                                            const float* __restrict__ y, unsigned char* __restrict__ Xb,
+                                                            float* __restrict__ partial, int* __restrict__ overflow)
+{
+    const long long nk8 = (nk + 7) / 8;
+    const long long total = ncb * 128 * nk8;
+    const int lane = threadIdx.x & 31, t = lane & 3, u = lane >> 2;
+    const bool vec = (ld & 3) == 0 && (((uintptr_t)X) & 15) == 0;
+    bool ovf = false;
+    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const long long g = w % nk8, cc = w / nk8;
+        const long long cb = cb0 + cc / 128;
+        const int c = (int)(cc % 128);
+        const long long col = cb * 128 + c, kb = g * 8 + u;
+        const long long r0 = kb * 32 + 8 * t;
+        float v[8], yy[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v[i] = 0.f; yy[i] = 0.f; }
+        if (col < p && kb < nk) {
+            const float* src = X + col * ld + r0;
+            const float mu = mean[col], f = inv[col];
+            if (r0 + 8 <= n) {
+                if (vec) {
+                    const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(src)), b = ld_stream_f4(reinterpret_cast<const float4*>(src) + 1);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = src[i];
+                }
+                const float4 ya = __ldg(reinterpret_cast<const float4*>(y + r0)), yb = __ldg(reinterpret_cast<const float4*>(y + r0) + 1);
+                yy[0] = ya.x; yy[1] = ya.y; yy[2] = ya.z; yy[3] = ya.w; yy[4] = yb.x; yy[5] = yb.y; yy[6] = yb.z; yy[7] = yb.w;
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fsub_rn(v[i], mu), f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (r0 + i < n) { v[i] = __fmul_rn(__fsub_rn(src[i], mu), f); yy[i] = y[r0 + i]; }
+            }
+        }
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d = __fmaf_rn(v[i], yy[i], d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) partial[cc * nk8 + g] = d;
+        if (kb >= nk) continue;
+        const float amax = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                                 fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+        ovf |= !(amax <= 65000.f);
+        uint4 h, l;
+        h.x = pack_half2(v[0], v[1]); h.y = pack_half2(v[2], v[3]); h.z = pack_half2(v[4], v[5]); h.w = pack_half2(v[6], v[7]);
+        const float2 f0 = unpack_half2(h.x), f1 = unpack_half2(h.y), f2 = unpack_half2(h.z), f3 = unpack_half2(h.w);
+        l.x = pack_half2(v[0] - f0.x, v[1] - f0.y); l.y = pack_half2(v[2] - f1.x, v[3] - f1.y);
+        l.z = pack_half2(v[4] - f2.x, v[5] - f2.y); l.w = pack_half2(v[6] - f3.x, v[7] - f3.y);
+        unsigned char* row = Xb + ((cb * nk + kb) * 128 + c) * 128;
+        *reinterpret_cast<uint4*>(row + 16 * t) = h;
+        *reinterpret_cast<uint4*>(row + 64 + 16 * t) = l;
+    }
+    if (ovf) atomicExch(overflow, 1);
+}
+
+// out[j] = sum_g partial[j][g], one warp per column, fixed order
+__global__ void __launch_bounds__(256) xty_reduce_kernel(const float* __restrict__ partial, long long ncols, long long nk8, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= ncols) return;
+    float s = 0.f;
+    for (long long g = lane; g < nk8; g += 32) s += partial[j * nk8 + g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[j] = s;
+}
+
+// ---- work distribution ---------------------------------------------------------------------------
+// Every tile is the sum of its canonical K-SLICES (H_SLICES of them, chunk aligned), always combined in
+// slice order: tile = ((P_0 + P_1) + P_2) + ...  -- whoever computes the slices.  Full rounds hand whole
+// tiles to the CTA pairs round-robin (the owner adds each finished slice to G in memory); the tiles of the
+// last, partial round are cut along K across the otherwise idle pairs, their slice sums go to a scratch
+// array and the pair that delivers a tile's last slice adds them up in slice order.  The result therefore
+// does not depend on how many tiles a launch covers (820 tiles over 74 pairs used to cost 12 rounds for
+// 11.08 rounds of work, and a 40-tile panel a whole round).
+constexpr int H_SLICES = 24;
+struct HWork {
+    int ntiles, npairs, rounds, tail, per_tile;   // tail tiles are shared by per_tile pairs each (0: no tail)
+    int nslices, nch;                             // canonical slices per tile, chunks per tile
+};
+__host__ __device__ __forceinline__ HWork h_work(int ntiles, int npairs, int nk)
+{
+    HWork w;
+    w.ntiles = ntiles; w.npairs = npairs;
+    w.rounds = ntiles / npairs;
+    w.tail = ntiles % npairs;
+    w.per_tile = w.tail ? npairs / w.tail : 0;
+    w.nch = (nk + CHUNK_STEPS - 1) / CHUNK_STEPS;
+    w.nslices = w.nch < H_SLICES ? (w.nch < 1 ? 1 : w.nch) : H_SLICES;
+    return w;
+}
+struct HItem { int tile, s0, s1, split, tt; };
+// item `i` of pair `pair`: i < rounds are whole tiles; i == rounds is the pair's share of the tail (if any)
+__device__ __forceinline__ bool h_item(const HWork& w, int pair, int i, HItem& it)
+{
+    if (i < w.rounds) { it.tile = pair + i * w.npairs; it.s0 = 0; it.s1 = w.nslices; it.split = 0; it.tt = 0; return true; }
+    if (i > w.rounds || w.tail == 0) return false;
+    if (w.per_tile <= 1) {
+        if (pair >= w.tail) return false;
+        it.tile = w.rounds * w.npairs + pair; it.s0 = 0; it.s1 = w.nslices; it.split = 0; it.tt = 0;
+        return true;
+    }
+    const int tt = pair / w.per_tile, sl = pair % w.per_tile;
+    if (tt >= w.tail) return false;
+    it.tile = w.rounds * w.npairs + tt; it.tt = tt; it.split = 1;
+    it.s0 = (int)((long long)sl * w.nslices / w.per_tile);
+    it.s1 = (int)((long long)(sl + 1) * w.nslices / w.per_tile);
+    return it.s1 > it.s0;
+}
+__device__ __forceinline__ int h_slice_chunk0(const HWork& w, int s) { return (int)((long long)s * w.nch / w.nslices); }
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H_THREADS, 1)
-gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles)
+gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles,
+                   float* __restrict__ scratch, int* __restrict__ counters)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -735,10 +861,12 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
     uint64_t* tmem_full = bars + 2 * H_STAGES;        // [2]        MMA commit (multicast) -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;             // [2]        leader's: epilogue warps of both CTAs -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const HWork W = h_work(ntiles, npairs, nk);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < H_STAGES; i++) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
@@ -754,7 +882,6 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nchunk = (nk + CHUNK_STEPS - 1) / CHUNK_STEPS;
 
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
 
@@ -762,10 +889,12 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
         // ================================ TMA producer (each CTA) =======================
         if (lane == 0) {
             Ring r;
-            for (int t = pair; t < ntiles; t += npairs) {
+            HItem it;
+            for (int i = 0; h_item(W, pair, i, it); i++) {
                 int I, J;
-                pair_tile_coords(t, I0, I, J);
-                for (int ks = 0; ks < nk; ks++) {
+                pair_tile_coords(it.tile, I0, I, J);
+                const int ks0 = h_slice_chunk0(W, it.s0) * CHUNK_STEPS, ks1 = min(nk, h_slice_chunk0(W, it.s1) * CHUNK_STEPS);
+                for (int ks = ks0; ks < ks1; ks++) {
                     mbar_wait(smem_u32(empty + r.idx), r.phase ^ 1u);
                     const uint32_t fb = mapa_rank(smem_u32(full + r.idx), 0);      // the leader's barrier counts both CTAs' bytes
                     if (rank == 0) mbar_expect_tx(smem_u32(full + r.idx), 2 * P2_STAGE);
@@ -781,9 +910,11 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
         // ================================ MMA issuer (leader CTA only) ================
         if (rank == 0 && lane == 0) {
             Ring q, acc;
-            for (int t = pair; t < ntiles; t += npairs) {
-                for (int ks = 0; ks < nk; ks++) {
-                    const int c = ks % CHUNK_STEPS;
+            HItem it;
+            for (int i = 0; h_item(W, pair, i, it); i++) {
+                const int ks0 = h_slice_chunk0(W, it.s0) * CHUNK_STEPS, ks1 = min(nk, h_slice_chunk0(W, it.s1) * CHUNK_STEPS);
+                for (int ks = ks0; ks < ks1; ks++) {
+                    const int c = ks % CHUNK_STEPS;                          // slices are chunk aligned
                     if (c == 0) {
                         mbar_wait_cluster(smem_u32(tmem_empty + acc.idx), acc.phase ^ 1u);
                         tc_fence_after();
@@ -802,7 +933,7 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
                         tc_mma_f16_pair(d, a_hi + off, b_lo + off, IDESC_F16, 1u);
                     }
                     tc_commit_pair(smem_u32(empty + q.idx));
-                    if (c == CHUNK_STEPS - 1 || ks == nk - 1) {
+                    if (c == CHUNK_STEPS - 1 || ks == ks1 - 1) {
                         tc_commit_pair(smem_u32(tmem_full + acc.idx));
                         acc.advance(2);
                     }
@@ -815,37 +946,93 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
         const int quad = warp & 3;
         const int half = (warp - 4) >> 2;                  // which 128 of the 256 accumulator columns
+        const int etid = threadIdx.x - 128;                // 0 .. 255 among the epilogue threads
+        const int rloc = quad * 32 + lane;                 // row within this CTA's 128 rows of the tile
         Ring acc;
         float sum[T2 / 2];
 #pragma unroll
         for (int c = 0; c < T2 / 2; c++) sum[c] = 0.f;
-        for (int t = pair; t < ntiles; t += npairs) {
+        HItem it;
+        for (int i = 0; h_item(W, pair, i, it); i++) {
             int I, J;
-            pair_tile_coords(t, I0, I, J);
-            const int row = I * T2 + (int)rank * 128 + quad * 32 + lane;
-            for (int ch = 0; ch < nchunk; ch++) {
-                mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
-                tc_fence_after();
-#pragma unroll
-                for (int cg = 0; cg < T2 / 2 / 32; cg++) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc.idx * T2 + half * (T2 / 2) + cg * 32);
-                    tc_ld32(taddr, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 32; c++) sum[cg * 32 + c] += __uint_as_float(v[c]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(smem_u32(tmem_empty + acc.idx), 0);   // one arrival per warp on the leader's barrier
-                acc.advance(2);
-            }
+            pair_tile_coords(it.tile, I0, I, J);
+            const int row = I * T2 + (int)rank * 128 + rloc;
             const int col0 = J * T2 + half * (T2 / 2);
             float* g = G + (size_t)row + (size_t)col0 * ld;
+            for (int sl = it.s0; sl < it.s1; sl++) {
+                const int ch0 = h_slice_chunk0(W, sl), ch1 = h_slice_chunk0(W, sl + 1);
+                for (int ch = ch0; ch < ch1; ch++) {
+                    mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
+                    tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < T2 / 2; c++) {
-                if (row < p && col0 + c < p) g[(size_t)c * ld] = sum[c];
-                sum[c] = 0.f;
+                    for (int cg = 0; cg < T2 / 2 / 32; cg++) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc.idx * T2 + half * (T2 / 2) + cg * 32);
+                        tc_ld32(taddr, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; c++) sum[cg * 32 + c] += __uint_as_float(v[c]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(smem_u32(tmem_empty + acc.idx), 0);   // one arrival per warp on the leader's barrier
+                    acc.advance(2);
+                }
+                // ---- slice `sl` is complete in `sum` ----
+                if (!it.split) {
+                    // owner of the whole tile: G = P_0, then G += P_s in slice order (same thread, same address)
+                    // (batches of 16 columns: the compiler must not hoist all 128 loads above the adds)
+#pragma unroll
+                    for (int c0 = 0; c0 < T2 / 2; c0 += 16) {
+                        float old[16];
+#pragma unroll
+                        for (int c = 0; c < 16; c++)
+                            old[c] = (sl != 0 && row < p && col0 + c0 + c < p) ? __ldcg(g + (size_t)(c0 + c) * ld) : 0.f;
+#pragma unroll
+                        for (int c = 0; c < 16; c++) {
+                            if (row < p && col0 + c0 + c < p) g[(size_t)(c0 + c) * ld] = __fadd_rn(old[c], sum[c0 + c]);
+                            sum[c0 + c] = 0.f;
+                        }
+                        asm volatile("" ::: "memory");
+                    }
+                } else {
+                    float* sc = scratch + ((size_t)(it.tt * W.nslices + sl) * 2 + rank) * (size_t)(128 * T2) + (size_t)(half * (T2 / 2)) * 128 + rloc;
+#pragma unroll
+                    for (int c = 0; c < T2 / 2; c++) { __stcg(sc + (size_t)c * 128, sum[c]); sum[c] = 0.f; }
+                }
+            }
+            if (it.split) {
+                // publish this pair's slices; the CTA that completes the tile adds all slices in slice order
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (etid == 0) {
+                    const int done = atomicAdd(counters + it.tt * 2 + (int)rank, it.s1 - it.s0) + (it.s1 - it.s0);
+                    *last_flag = (done == W.nslices) ? 1 : 0;
+                    if (done == W.nslices) counters[it.tt * 2 + (int)rank] = 0;          // ready for the next launch
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (*last_flag) {
+                    __threadfence();
+                    const float* sc = scratch + ((size_t)(it.tt * W.nslices) * 2 + rank) * (size_t)(128 * T2) + (size_t)(half * (T2 / 2)) * 128 + rloc;
+                    for (int sl = 0; sl < W.nslices; sl++) {
+                        const float* ss = sc + (size_t)sl * 2 * (128 * T2);
+#pragma unroll
+                        for (int c0 = 0; c0 < T2 / 2; c0 += 16) {
+                            float v[16];
+#pragma unroll
+                            for (int c = 0; c < 16; c++) v[c] = __ldcg(ss + (size_t)(c0 + c) * 128);
+#pragma unroll
+                            for (int c = 0; c < 16; c++) sum[c0 + c] = __fadd_rn(sum[c0 + c], v[c]);   // sum starts at 0: 0 + P_0 = P_0 exactly
+                            asm volatile("" ::: "memory");
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < T2 / 2; c++) {
+                        if (row < p && col0 + c < p) g[(size_t)c * ld] = sum[c];
+                        sum[c] = 0.f;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");       // last_flag is reused by the next item
             }
         }
     }
@@ -968,6 +1155,29 @@ void gram_split_f16_blocked(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 
     KERNEL_CHECK();
 }
 
+size_t gram_f16_xty_work_floats(i64 n, i64 ncols)
+{
+    const i64 nk8 = ((n + 31) / 32 + 7) / 8;
+    return (size_t)(((ncols + 127) / 128) * 128) * (size_t)nk8;
+}
+
+void gram_std_split_xty(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i64 col_begin, i64 col_end,
+                        const float* mean, const float* inv, const float* y, void* Xb, float* xty, float* work)
+{
+    if (col_end < 0) col_end = p;
+    if (col_begin % 128 != 0) throw ArgError("gram_std_split_xty: panels start at a multiple of 128 columns");
+    if (col_end <= col_begin) return;
+    const long long nk = (n + 31) / 32, nk8 = (nk + 7) / 8, cb0 = col_begin / 128, ncb = (col_end + 127) / 128 - cb0;
+    const long long tasks = ncb * 128 * nk8;
+    const unsigned grid = (unsigned)std::min<long long>((tasks + 7) / 8, (long long)sm_count() * 32);
+    std_split_xty_kernel<<<grid, 256, 0, s>>>(X, (long long)n, (long long)ldx, (long long)p, nk, cb0, ncb, mean, inv, y,
+                                              (unsigned char*)Xb, work, overflow_flag());
+    KERNEL_CHECK();
+    const long long ncols = col_end - col_begin;
+    xty_reduce_kernel<<<(unsigned)((ncols + 7) / 8), 256, 0, s>>>(work, ncols, nk8, xty + col_begin);
+    KERNEL_CHECK();
+}
+
 bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G, i64 ld, i64 col_begin, i64 col_end, bool mirror)
 {
     if ((((uintptr_t)Xb) & 127) != 0 || !gram_f16_usable(n, p)) return false;
@@ -987,8 +1197,24 @@ bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G,
             CUDA_CHECK(cudaFuncSetAttribute(gram_pair_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
             attr = true;
         }
-        const int grid = 2 * std::min(ntiles, sm_count() / 2);
-        gram_pair_h_kernel<<<grid, H_THREADS, H_SMEM, s>>>(map, G, (int)p, (long long)ld, (int)nk, I0, ntiles);
+        const int npairs = sm_count() / 2;                       // tail tiles are cut along K over the idle pairs
+        const HWork w = h_work(ntiles, npairs, (int)nk);
+        // scratch for the slice sums of K-split tail tiles + self-resetting arrival counters
+        static float* scratch = nullptr;
+        static size_t scratch_floats = 0;
+        static int* counters = nullptr;
+        if (!counters) {
+            CUDA_CHECK(cudaMalloc(&counters, sizeof(int) * 2 * 256));
+            CUDA_CHECK(cudaMemset(counters, 0, sizeof(int) * 2 * 256));
+        }
+        const size_t need = w.per_tile > 1 ? (size_t)w.tail * w.nslices * 2 * 128 * T2 : 0;
+        if (need > scratch_floats) {
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            if (scratch) CUDA_CHECK(cudaFree(scratch));
+            CUDA_CHECK(cudaMalloc(&scratch, need * sizeof(float)));
+            scratch_floats = need;
+        }
+        gram_pair_h_kernel<<<2 * npairs, H_THREADS, H_SMEM, s>>>(map, G, (int)p, (long long)ld, (int)nk, I0, ntiles, scratch, counters);
         KERNEL_CHECK();
     }
     if (mirror) {

@@ -39,6 +39,12 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
 bool gram_f16_usable(i64 n, i64 p);
 size_t gram_f16_blocked_bytes(i64 n, i64 p);
 void gram_split_f16_blocked(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i64 col_begin, i64 col_end, void* Xb);
+// DataStd flag 3 fused with the split: reads the RAW columns [col_begin, col_end) of X once, applies
+// (x - mean[j]) * inv[j] (col_apply's arithmetic), writes the blocked operands and xty[j] = sum_i x_std(i,j) y(i)
+// (y: the standardised response).  work: gram_f16_xty_work_floats(n, col_end - col_begin) floats.
+size_t gram_f16_xty_work_floats(i64 n, i64 ncols);
+void gram_std_split_xty(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i64 col_begin, i64 col_end,
+                        const float* mean, const float* inv, const float* y, void* Xb, float* xty, float* work);
 bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G, i64 ld,
                          i64 col_begin = 0, i64 col_end = -1, bool mirror = true);
 // synchronises `s`; true (and the flag is cleared) if an fp16 split since the last call met |x| > 65000

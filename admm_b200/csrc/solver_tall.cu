@@ -91,6 +91,20 @@ static void standardize_cols_sharded(cudaStream_t s, const float* X_in, i64 ld_i
     }
 }
 
+// DataStd flag 3 statistics of a column panel without the apply step (the fp16 Gram path applies them while
+// it splits the operands): meanX, scaleX and inv = 1 / scaleX, exactly as in standardize_cols_sharded case 3.
+static void standardize_stats3_sharded(cudaStream_t s, const float* X_in, i64 ld_in, i64 n_local, i64 n_total, i64 pc,
+                                       float* d_meanX, float* d_scaleX, float* d_inv, float* tmp)
+{
+    float* sums = tmp;
+    column_sums<float>(s, X_in, n_local, pc, ld_in, sums);
+    allreduce_sum(s, sums, pc);
+    mean_from_sums<float>(s, sums, pc, n_total, d_meanX);
+    column_center_sumsq<float>(s, const_cast<float*>(X_in), n_local, pc, ld_in, d_meanX, d_scaleX, false);
+    allreduce_sum(s, d_scaleX, pc);
+    scale_from_sumsq<float>(s, d_scaleX, pc, n_total, false, d_scaleX, d_inv);
+}
+
 static void fetch_std_stats(cudaStream_t s, i64 p, int flag, const float* d_meanX, const float* d_scaleX, StdStats& st)
 {
     st.meanX.assign(p, 0.f);
@@ -153,9 +167,14 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     const bool use_f16 = want_tensor && !gram_env && flag == 3 && (double)n < 4.0e9 && gram_f16_usable(n_local, p);
     const i64 ldx = (n_local + 3) & ~(i64)3;
     const bool padded = ldx != n_local;
-    DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
+    // fp16 path on device-resident input: the raw columns are read in place (statistics, then one fused
+    // standardise + X'y + split pass); no float32 working copy exists at all
+    const bool need_copy = !(use_f16 && d->dtype == B200ADMM_F32_DEVICE);
+    DevBuf<float> Xs, ys(n_local), Xtmp;
+    if (need_copy) Xs.alloc((size_t)ldx * (size_t)p);
     DevBuf<unsigned char> Xb;
-    if (use_f16) Xb.alloc(gram_f16_blocked_bytes(n_local, p));
+    DevBuf<float> d_inv, xty_work;
+    if (use_f16) { Xb.alloc(gram_f16_blocked_bytes(n_local, p)); d_inv.alloc(p); }
     DevBuf<float> d_meanX(p), d_scaleX(p);
     DevBuf<float> XY(ld);
     DevBuf<float> G((size_t)p * (size_t)ld);
@@ -179,8 +198,20 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         i64 pw = (i64)(((size_t)3 << 30) / ((size_t)n_local * esz));          // ~3 GB of host data per panel
         if (const char* pw_env = getenv("B200ADMM_PANEL_COLS")) pw = atoll(pw_env);     // tests: force several panels
         pw = std::max<i64>(256, (pw / 256) * 256);                        // whole 256-column row blocks of the pair kernel
-        const int npan = (int)((p + pw - 1) / pw);
+        // Panel schedule: wide panels first; the last ~1000 columns in single 256-column row blocks.  Whatever
+        // Gram work belongs to the final panel starts only after the copy has ended (its share of the whole
+        // is 2 w / p for a panel of w columns), and a 256-column launch is no longer wasteful: its <= 40 tiles
+        // are cut along K over all CTA pairs.
+        std::vector<i64> pan_begin;
+        for (i64 c = 0; c < p;) {
+            pan_begin.push_back(c);
+            const i64 left = p - c;
+            c += (left > pw + 768 || pw <= 256) ? std::min(pw, left) : std::min<i64>(256, left);
+        }
+        pan_begin.push_back(p);
+        const int npan = (int)pan_begin.size() - 1;
         DevBuf<float> tmp(2 * pw + 8);
+        if (use_f16) xty_work.alloc(gram_f16_xty_work_floats(n_local, pw));
         DevBuf<double> slab[2];
         if (esz == 8) { slab[0].alloc((size_t)n_local * (size_t)pw); slab[1].alloc((size_t)n_local * (size_t)pw); }
         std::vector<cudaEvent_t> landed(npan), freed(2);
@@ -192,7 +223,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         CUDA_CHECK(cudaEventRecord(start_ev, s));
         CUDA_CHECK(cudaStreamWaitEvent(cs, start_ev, 0));
         for (int k = 0; k < npan; k++) {
-            const i64 c0 = k * pw, pc = std::min(pw, p - c0);
+            const i64 c0 = pan_begin[k], pc = pan_begin[k + 1] - c0;
             float* dstp = Xs.p + c0 * ldx;
             if (esz == 4) {
                 const float* src = (const float*)d->x + c0 * n_local;
@@ -210,14 +241,15 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
                 else for (i64 j = 0; j < pc; j++) convert_f64_to_f32(s, slab[k & 1].p + j * n_local, dstp + j * ldx, (size_t)n_local);
                 CUDA_CHECK(cudaEventRecord(freed[k & 1], s));
             }
-            standardize_cols_sharded(s, dstp, ldx, dstp, ldx, n_local, n, pc, flag, d_meanX.p + c0, d_scaleX.p + c0, tmp.p);
-            gemv_t<float>(s, dstp, n_local, pc, ldx, ys.p, XY.p + c0);
             bool ok;
             if (use_f16) {
-                gram_split_f16_blocked(s, Xs.p, n_local, ldx, p, c0, c0 + pc, Xb.p);
+                standardize_stats3_sharded(s, dstp, ldx, n_local, n, pc, d_meanX.p + c0, d_scaleX.p + c0, d_inv.p + c0, tmp.p);
+                gram_std_split_xty(s, Xs.p, n_local, ldx, p, c0, c0 + pc, d_meanX.p, d_inv.p, ys.p, Xb.p, XY.p, xty_work.p);
                 gram_kernel_time.begin();
                 ok = gram_tn_f16_blocked(s, Xb.p, n_local, p, G.p, ld, c0, c0 + pc, k == npan - 1);
             } else {
+                standardize_cols_sharded(s, dstp, ldx, dstp, ldx, n_local, n, pc, flag, d_meanX.p + c0, d_scaleX.p + c0, tmp.p);
+                gemv_t<float>(s, dstp, n_local, pc, ldx, ys.p, XY.p + c0);
                 gram_kernel_time.begin();
                 ok = gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode, c0, c0 + pc, k == npan - 1);
             }
@@ -239,7 +271,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     const float* X_in = Xs.p;
     i64 ld_in = ldx;
     tm.start();
-    if (padded) Xs.zero(s);
+    if (padded && need_copy) Xs.zero(s);
     if (d->dtype == B200ADMM_F32_DEVICE) {
         X_in = (const float*)d->x;                      // standardised out of place, caller's copy untouched
         ld_in = n_local;
@@ -254,25 +286,36 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
 
     // ---- DataStd -----------------------------------------------------------------------------
     tm.start();
-    standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    if (use_f16) {
+        // statistics only: the apply step is fused with X'y and the operand split below
+        DevBuf<float> tmp(2 * p + 8);
+        standardize_y_sharded(s, ys.p, n_local, n, flag, st);
+        standardize_stats3_sharded(s, X_in, ld_in, n_local, n, p, d_meanX.p, d_scaleX.p, d_inv.p, tmp.p);
+        fetch_std_stats(s, p, flag, d_meanX.p, d_scaleX.p, st);
+    } else {
+        standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    }
     T.standardize = tm.stop();
-    Xtmp.release();
+    if (!use_f16) Xtmp.release();
 
     // ---- X'y, lambda0, Gram ------------------------------------------------------------------
     tm.start();
     XY.zero(s);
-    gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, XY.p);
-    allreduce_sum(s, XY.p, p);
+    if (!use_f16) gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, XY.p);
     G.zero(s);
     bool on_tensor = false;
     if (use_f16) {
-        gram_split_f16_blocked(s, Xs.p, n_local, ldx, p, 0, p, Xb.p);
+        xty_work.alloc(gram_f16_xty_work_floats(n_local, p));
+        gram_std_split_xty(s, X_in, n_local, ld_in, p, 0, p, d_meanX.p, d_inv.p, ys.p, Xb.p, XY.p, xty_work.p);
+        Xtmp.release();
+        allreduce_sum(s, XY.p, p);
         gram_kernel_time.begin();
         on_tensor = gram_tn_f16_blocked(s, Xb.p, n_local, p, G.p, ld);
         gram_kernel_time.end();
         if (!on_tensor) throw CudaError("fp16 Gram kernel declined the shape");
         if (gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
     } else {
+        allreduce_sum(s, XY.p, p);
         gram_kernel_time.begin();
         on_tensor = want_tensor && gram_tn_tensor(s, Xs.p, n_local, ldx, p, G.p, ld, split_mode);
         if (!on_tensor)     // CUDA-core path (shapes the tensor kernel does not take)
