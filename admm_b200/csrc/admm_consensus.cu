@@ -230,7 +230,11 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
             b.Kinv.alloc((size_t)p * (size_t)ld);
             b.Kinv.zero(s);
             // (the tensor kernel declines block starts that are not 16-byte aligned; CUDA cores then)
-            const bool on_tensor = want_tensor && gram_tn_tensor(s, A, b.rows, ldx, p, b.Kinv.p, ld, 1);
+            // flag 3 (centred, unit-norm columns, |x| <= sqrt(n)): fp16 hi / lo operands, otherwise the TF32 split
+            const int split = (flag == 3 && (double)n < 4.0e9 && !gram_env) ? GRAM_SPLIT_F16 : GRAM_SPLIT_TF32;
+            const bool on_tensor = want_tensor && gram_tn_tensor(s, A, b.rows, ldx, p, b.Kinv.p, ld, split);
+            if (on_tensor && split == GRAM_SPLIT_F16 && gram_f16_overflowed(s))
+                throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
             if (!on_tensor)
                 gemm<float>(s, true, false, p, p, b.rows, 1.f, A, ldx, A, ldx, 0.f, b.Kinv.p, ld, GEMM_LOWER | GEMM_MIRROR);
             add_to_diagonal(s, b.Kinv.p, ld, p, frho);

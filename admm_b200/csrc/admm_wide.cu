@@ -342,7 +342,10 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             if (tg.y <= 65535) {
                 transpose_kernel<<<tg, 256, 0, s>>>(X, n, p, ldx, Y.p, ldy);
                 KERNEL_CHECK();
-                on_tensor = gram_tn_tensor(s, Y.p, p, ldy, n, Gn.p, n, 1);
+                const int split = (flag == 3 && !gram_env) ? GRAM_SPLIT_F16 : GRAM_SPLIT_TF32;   // |x_std| <= sqrt(n) under flag 3
+                on_tensor = gram_tn_tensor(s, Y.p, p, ldy, n, Gn.p, n, split);
+                if (on_tensor && split == GRAM_SPLIT_F16 && gram_f16_overflowed(s))
+                    throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
                 CUDA_CHECK(cudaStreamSynchronize(s));
             }
         }
