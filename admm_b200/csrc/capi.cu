@@ -333,7 +333,7 @@ void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* k
     const bool hit = use_graph && fg.exec && fg.a == a && fg.W == W && fg.keep == keep_factor && fg.p == p && fg.ld == ld;
     if (!hit) {
         if (fg.exec) { cudaGraphExecDestroy(fg.exec); fg.exec = nullptr; }
-        if (fg.p != p) { fg.work.alloc(chol_work<T>(p)); fg.tmp.alloc((size_t)p * 128); }
+        if (fg.p != p) { fg.work.alloc(chol_work<T>(p)); fg.tmp.alloc(tri_inverse_tmp(p)); }
         if (!fg.info.p) fg.info.alloc(1);
         fg.a = a; fg.W = W; fg.keep = keep_factor; fg.p = p; fg.ld = ld;
         cudaGraph_t graph = nullptr;

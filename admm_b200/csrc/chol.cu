@@ -16,6 +16,9 @@
 //   gram_of_lower     K^-1 = W' W (full symmetric storage).
 #include "common.cuh"
 #include "kernels.h"
+#include <cstring>
+#include <cstdlib>
+#include <type_traits>
 
 namespace b200 {
 
@@ -144,16 +147,40 @@ __global__ void __launch_bounds__(1024) chol_solve_vec_kernel(const T* __restric
     }
 }
 
+// out (cols x rows, ld ldo) = in' for in (rows x cols, ld ldi): 32 x 32 tiles through shared memory
+template <class T>
+__global__ void __launch_bounds__(256) transpose_block_kernel(const T* __restrict__ in, i64 ldi, i64 rows, i64 cols, T* __restrict__ out, i64 ldo)
+{
+    __shared__ T tile[32][33];
+    const i64 r0 = (i64)blockIdx.x * 32, c0 = (i64)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int c = ty; c < 32; c += 8)
+        tile[c][tx] = (r0 + tx < rows && c0 + c < cols) ? in[(r0 + tx) + (c0 + c) * ldi] : T(0);
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (c0 + tx < cols && r0 + r < rows) out[(c0 + tx) + (r0 + r) * ldo] = tile[tx][r];
+}
+
 }  // namespace
 
-// work layout: [nblk * NB * NB] inverse diagonal blocks, then [p * NB] panel scratch
+// Two-level blocking.  Inner blocks of NB = 128 columns are factored as before (diagonal block in shared
+// memory, panel = A21 inv(L11)'), but their rank-128 updates are confined to the current OUTER panel of
+// OB = 1024 columns; the rest of the matrix then receives ONE rank-1024 update per outer panel,
+// A22 -= L21 L21', which for float runs on the tensor cores: L21 is transposed into a K-major scratch
+// array and handed to the tcgen05 3xTF32 CTA-pair Gram kernel in subtract mode (fp32-accurate; 97 % of
+// the factorisation's flops at p = 1e4).  With single-level blocking the same flops were 79 rank-128
+// CUDA-core updates at ~12 TFLOP/s.
+constexpr int OB = 1024;
+
+// work layout: [nblk * NB * NB] inverse diagonal blocks, [p * NB] panel scratch, [p * OB] transposed outer panel
 template <class T> size_t chol_work(i64 p)
 {
     const i64 nblk = (p + NB - 1) / NB;
-    return (size_t)(nblk * NB * NB + p * NB);
+    return (size_t)(nblk * NB * NB + p * NB + p * OB);
 }
 template size_t chol_work<float>(i64);
 template size_t chol_work<double>(i64);
+size_t tri_inverse_tmp(i64 p) { return (size_t)p * OB; }
 
 template <class T>
 void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev)
@@ -161,6 +188,7 @@ void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev)
     const i64 nblk = (p + NB - 1) / NB;
     T* Dinv = work;
     T* panel = work + nblk * NB * NB;
+    T* Lt = panel + p * NB;                                       // OB x m2, ld = OB
     const int winv_in_smem = sizeof(T) == 4 ? 1 : 0;             // two 128 x 129 tiles: 132 KB in float, too large in double
     const size_t smem = sizeof(T) * NB * (NB + 1) * (winv_in_smem ? 2 : 1);
     static bool attr_done_f = false, attr_done_d = false;
@@ -169,45 +197,76 @@ void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev)
         CUDA_CHECK(cudaFuncSetAttribute(chol_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
+    const char* tenv = getenv("B200ADMM_FACTOR_TENSOR");
+    const bool tensor_ok = std::is_same<T, float>::value && !(tenv && !strcmp(tenv, "0"));
     CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
-    for (i64 b = 0; b < nblk; b++) {
-        const i64 k0 = b * NB;
-        const int kb = (int)std::min<i64>(NB, p - k0);
-        T* Akk = A + k0 + k0 * lda;
-        chol_diag_kernel<T><<<1, DIAG_THREADS, smem, s>>>(Akk, lda, kb, (int)k0, Dinv + b * NB * NB, info_dev, winv_in_smem);
-        KERNEL_CHECK();
-        const i64 m = p - k0 - kb;
-        if (m <= 0) break;
-        T* A21 = A + (k0 + kb) + k0 * lda;
-        // L21 = A21 * inv(L11)'
-        gemm<T>(s, false, true, m, kb, kb, T(1), A21, lda, Dinv + b * NB * NB, NB, T(0), panel, m, 0);
-        copy_block<T>(s, panel, m, A21, lda, m, kb);
-        // A22 -= L21 L21'
-        T* A22 = A + (k0 + kb) + (k0 + kb) * lda;
-        gemm<T>(s, false, true, m, m, kb, T(-1), panel, m, panel, m, T(1), A22, lda, GEMM_LOWER);
+    for (i64 k0 = 0; k0 < p; k0 += OB) {
+        const i64 kend = std::min<i64>(p, k0 + OB), ob = kend - k0;
+        for (i64 j0 = k0; j0 < kend; j0 += NB) {
+            const i64 b = j0 / NB;
+            const int kb = (int)std::min<i64>(NB, p - j0);
+            T* Akk = A + j0 + j0 * lda;
+            chol_diag_kernel<T><<<1, DIAG_THREADS, smem, s>>>(Akk, lda, kb, (int)j0, Dinv + b * NB * NB, info_dev, winv_in_smem);
+            KERNEL_CHECK();
+            const i64 m = p - j0 - kb;
+            if (m <= 0) break;
+            T* A21 = A + (j0 + kb) + j0 * lda;
+            // L21 = A21 * inv(L11)'
+            gemm<T>(s, false, true, m, kb, kb, T(1), A21, lda, Dinv + b * NB * NB, NB, T(0), panel, m, 0);
+            copy_block<T>(s, panel, m, A21, lda, m, kb);
+            // inside the outer panel: A(j0+kb.., j0+kb..kend) -= L21 L21(0..w,:)'   (lower part of the leading square)
+            const i64 w = kend - (j0 + kb);
+            if (w > 0)
+                gemm<T>(s, false, true, m, w, kb, T(-1), panel, m, panel, m, T(1), A + (j0 + kb) + (j0 + kb) * lda, lda, GEMM_LOWER);
+        }
+        const i64 m2 = p - kend;
+        if (m2 <= 0) break;
+        const T* L21 = A + kend + k0 * lda;                        // m2 x ob
+        T* A22 = A + kend + kend * lda;
+        bool on_tensor = false;
+        if (tensor_ok && m2 >= 256 && ob % 4 == 0) {
+            dim3 tg((unsigned)((m2 + 31) / 32), (unsigned)((ob + 31) / 32));
+            transpose_block_kernel<T><<<tg, 256, 0, s>>>(L21, lda, m2, ob, Lt, ob);
+            KERNEL_CHECK();
+            on_tensor = gram_tn_tensor_sub(s, reinterpret_cast<const float*>(Lt), ob, ob, m2, reinterpret_cast<float*>(A22), lda);
+        }
+        if (!on_tensor)
+            gemm<T>(s, false, true, m2, m2, ob, T(-1), L21, lda, L21, lda, T(1), A22, lda, GEMM_LOWER);
     }
 }
 template void chol_lower<float>(cudaStream_t, float*, i64, i64, float*, int*);
 template void chol_lower<double>(cudaStream_t, double*, i64, i64, double*, int*);
 
-// W <- L^-1.  `work` is chol_lower's workspace (inverse diagonal blocks); tmp: p * NB entries.
+// W <- L^-1.  `work` is chol_lower's workspace (inverse diagonal blocks); tmp: tri_inverse_tmp(p) entries.
+// Two-level as well: the OB x OB diagonal block of W is inverted with the NB recursion, then the whole
+// block column below it follows from two products with N = OB columns,  T = L21 W11,  W21 = -W22 T,
+// wide enough to fill the chip (the NB-wide products of the one-level recursion ran on 40-80 CTAs).
 template <class T>
 void tri_inverse_lower(cudaStream_t s, const T* L, i64 p, i64 lda, const T* work, T* W, i64 ldw, T* tmp)
 {
-    const i64 nblk = (p + NB - 1) / NB;
     CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(T) * (size_t)ldw * (size_t)p, s));
-    for (i64 b = nblk - 1; b >= 0; b--) {
-        const i64 j0 = b * NB;
-        const int kb = (int)std::min<i64>(NB, p - j0);
-        const T* Dinv = work + b * NB * NB;
-        copy_block<T>(s, Dinv, NB, W + j0 + j0 * ldw, ldw, kb, kb);
-        const i64 m = p - j0 - kb;
-        if (m <= 0) continue;
-        // T = L21 * inv(L11)
-        gemm<T>(s, false, false, m, kb, kb, T(1), L + (j0 + kb) + j0 * lda, lda, Dinv, NB, T(0), tmp, m, 0);
-        // W21 = - W22 * T      (W22 lower triangular, already final)
-        gemm<T>(s, false, false, m, kb, m, T(-1), W + (j0 + kb) + (j0 + kb) * ldw, ldw, tmp, m, T(0),
-                W + (j0 + kb) + j0 * ldw, ldw, GEMM_A_LOWER_TRI);
+    const i64 nouter = (p + OB - 1) / OB;
+    for (i64 o = nouter - 1; o >= 0; o--) {
+        const i64 k0 = o * OB, kend = std::min<i64>(p, k0 + OB), ob = kend - k0;
+        // W11 = inv(L11), NB block columns right to left inside the outer block
+        const i64 nin = (ob + NB - 1) / NB;
+        for (i64 bi = nin - 1; bi >= 0; bi--) {
+            const i64 j0 = k0 + bi * NB;
+            const int kb = (int)std::min<i64>(NB, kend - j0);
+            const T* Dinv = work + (j0 / NB) * NB * NB;
+            copy_block<T>(s, Dinv, NB, W + j0 + j0 * ldw, ldw, kb, kb);
+            const i64 m = kend - j0 - kb;
+            if (m <= 0) continue;
+            gemm<T>(s, false, false, m, kb, kb, T(1), L + (j0 + kb) + j0 * lda, lda, Dinv, NB, T(0), tmp, m, 0);
+            gemm<T>(s, false, false, m, kb, m, T(-1), W + (j0 + kb) + (j0 + kb) * ldw, ldw, tmp, m, T(0),
+                    W + (j0 + kb) + j0 * ldw, ldw, GEMM_A_LOWER_TRI);
+        }
+        const i64 m2 = p - kend;
+        if (m2 <= 0) continue;
+        // T = L21 * W11   (W11 lower triangular)
+        gemm<T>(s, false, false, m2, ob, ob, T(1), L + kend + k0 * lda, lda, W + k0 + k0 * ldw, ldw, T(0), tmp, m2, GEMM_B_LOWER_TRI);
+        // W21 = - W22 * T  (W22 lower triangular, already final)
+        gemm<T>(s, false, false, m2, ob, m2, T(-1), W + kend + kend * ldw, ldw, tmp, m2, T(0), W + kend + k0 * ldw, ldw, GEMM_A_LOWER_TRI);
     }
 }
 template void tri_inverse_lower<float>(cudaStream_t, const float*, i64, i64, const float*, float*, i64, float*);

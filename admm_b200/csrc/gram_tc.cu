@@ -442,7 +442,7 @@ __device__ __forceinline__ void pair_tile_coords(int t, int I0, int& I, int& J)
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
-gram_pair_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles)
+gram_pair_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles, int subtract)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -595,10 +595,26 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G,
             }
             const int col0 = J * T2 + half * (T2 / 2);
             float* g = G + (size_t)row + (size_t)col0 * ld;
+            if (subtract) {
+                // C -= X'X (trailing update of the blocked Cholesky): batches of 16 so the loads stay few in flight
 #pragma unroll
-            for (int c = 0; c < T2 / 2; c++) {
-                if (row < p && col0 + c < p) g[(size_t)c * ld] = sum[c];
-                sum[c] = 0.f;
+                for (int c0 = 0; c0 < T2 / 2; c0 += 16) {
+                    float old[16];
+#pragma unroll
+                    for (int c = 0; c < 16; c++) old[c] = (row < p && col0 + c0 + c < p) ? g[(size_t)(c0 + c) * ld] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) {
+                        if (row < p && col0 + c0 + c < p) g[(size_t)(c0 + c) * ld] = __fsub_rn(old[c], sum[c0 + c]);
+                        sum[c0 + c] = 0.f;
+                    }
+                    asm volatile("" ::: "memory");
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < T2 / 2; c++) {
+                    if (row < p && col0 + c < p) g[(size_t)c * ld] = sum[c];
+                    sum[c] = 0.f;
+                }
             }
         }
     }
@@ -1225,6 +1241,27 @@ bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G,
     return true;
 }
 
+bool gram_tn_tensor_sub(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* C, i64 ld)
+{
+    if (ldx % 4 != 0 || (((uintptr_t)X) & 15) != 0 || n < 1 || p < 256 || (sm_count() % 2 != 0)) return false;
+    if (n >= 2147483647LL - BK || p >= 2147483647LL - T2) return false;
+    const char* kenv = getenv("B200ADMM_GRAM_KERNEL");
+    if (kenv && !strcmp(kenv, "1cta")) return false;
+    const int nk = (int)((n + BK - 1) / BK), nb = (int)((p + T2 - 1) / T2);
+    const int ntiles = nb * (nb + 1) / 2;
+    CUtensorMap map;
+    make_map(&map, X, n, ldx, p, 128);
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+        attr = true;
+    }
+    const int grid = 2 * std::min(ntiles, sm_count() / 2);
+    gram_pair_kernel<<<grid, 512, P2_SMEM, s>>>(map, C, (int)p, (long long)ld, nk, 0, ntiles, 1);
+    KERNEL_CHECK();
+    return true;
+}
+
 // Writes the full symmetric p x p matrix into G (leading dimension ld).
 bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* G, i64 ld, int split,
                     i64 col_begin, i64 col_end, bool mirror)
@@ -1258,7 +1295,7 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
                 attr2 = true;
             }
             const int grid = 2 * std::min(ntiles, sm_count() / 2);
-            gram_pair_kernel<<<grid, 512, P2_SMEM, s>>>(map, G, (int)p, (long long)ld, nk, I0, ntiles);
+            gram_pair_kernel<<<grid, 512, P2_SMEM, s>>>(map, G, (int)p, (long long)ld, nk, I0, ntiles, 0);
             KERNEL_CHECK();
         }
     } else {

@@ -47,6 +47,10 @@ void gram_std_split_xty(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i
                         const float* mean, const float* inv, const float* y, void* Xb, float* xty, float* work);
 bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G, i64 ld,
                          i64 col_begin = 0, i64 col_end = -1, bool mirror = true);
+// C (p x p, ld) -= X'X on the lower-triangle tiles (3xTF32 CTA-pair kernel, subtract epilogue; the strict upper
+// part of the diagonal tiles is overwritten with values nobody reads): the rank-n update of the blocked Cholesky.
+// X: n x p column-major, ldx % 4 == 0, p >= 256.  Returns false if the shape is not taken.
+bool gram_tn_tensor_sub(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* C, i64 ld);
 // synchronises `s`; true (and the flag is cleared) if an fp16 split since the last call met |x| > 65000
 bool gram_f16_overflowed(cudaStream_t s);
 
@@ -79,6 +83,7 @@ void convert_f64_to_f32(cudaStream_t s, const double* in, float* out, size_t cou
 template <class T> size_t chol_work(i64 p);
 template <class T> void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work, int* info_dev);
 // W (p x p, zero-initialised by the callee) <- L^-1 given the factor in A and chol's `work`
+size_t tri_inverse_tmp(i64 p);      // entries of tri_inverse_lower's `tmp`
 template <class T> void tri_inverse_lower(cudaStream_t s, const T* L, i64 p, i64 lda, const T* work, T* W, i64 ldw, T* tmp);
 // Kinv (p x p, full symmetric) <- W' W
 template <class T> void gram_of_lower(cudaStream_t s, const T* W, i64 p, i64 ldw, T* Kinv, i64 ldk);

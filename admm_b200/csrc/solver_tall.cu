@@ -367,7 +367,9 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     tm.start();
     add_to_diagonal(s, G.p, ld, p, (float)rho);
     {
-        DevBuf<float> W((size_t)p * (size_t)ld);
+        // (+64: a size class of its own, so the block cache can never hand G's block out as W or the reverse --
+        // the cached factor graph is keyed on both pointers)
+        DevBuf<float> W((size_t)p * (size_t)ld + 64);
         int info = 0;
         spd_inverse_f32(s, G.p, p, ld, W.p, &info);
     }
