@@ -227,6 +227,35 @@ def test_too_few_variables_is_an_error(A):
     assert e.value.code == -5
 
 
+def test_kkt_standardised_path_at_scale(A):
+    """Size-independent property at a size that exercises the whole production path of the headline config
+    (DataStd flag 3 -> fused standardise / X'y / fp16 operand split -> CTA-pair Gram with full rounds and a
+    K-split tail (153 tiles over 74 pairs) -> graph-replayed factorisation -> persistent path kernel): the
+    returned coefficients satisfy the lasso optimality conditions of the standardised problem,
+    |x_j'(y - b0 - X b)| / (n sd_j) <= lambda with equality and matching sign on the support."""
+    import torch
+    n, p = 200_000, 4352
+    g = torch.Generator(device="cuda").manual_seed(77)
+    X = torch.randn((p, n), device="cuda", dtype=torch.float32, generator=g) * 2.0 + 0.5       # column-major n x p
+    bt = torch.zeros(p, device="cuda", dtype=torch.float32)
+    bt[:40] = torch.rand(40, device="cuda", generator=g) + 0.2
+    y = X.t() @ bt + torch.randn(n, device="cuda", generator=g) + 3.0
+    f0 = A.admm_lasso(X.t(), y).penalty(nlambda=2).opts(maxit=1).fit()
+    lam = [0.2 * float(f0.lambda_[0]), 0.02 * float(f0.lambda_[0])]
+    f = A.admm_lasso(X.t(), y).penalty(lam).opts(eps_abs=1e-7, eps_rel=1e-7).fit()
+    B = torch.from_numpy(dense(f.beta)).cuda()                           # (p + 1) x 2, float64
+    Xd = X.double()
+    sd = Xd.std(dim=1, unbiased=False)
+    for k, lk in enumerate(lam):
+        r = y.double() - B[0, k] - Xd.t() @ B[1:, k]
+        assert abs(float(r.mean())) < 1e-5
+        grad = (Xd @ r) / n / sd
+        s = B[1:, k] != 0
+        assert int(s.sum()) >= 40
+        assert float(grad.abs().max()) <= lk * (1 + 2e-3)
+        assert torch.allclose(grad[s], lk * torch.sign(B[1:, k][s]), rtol=5e-3, atol=0)
+
+
 def test_kkt_at_moderate_size(A):
     """Size-independent property: the solution satisfies the lasso optimality conditions
     |X_j'(y - X b)| <= n*lambda (+tol), with equality and matching sign on the support."""
