@@ -26,5 +26,19 @@ void allreduce_sum(cudaStream_t s, float* buf, size_t count);
 void allreduce_sum(cudaStream_t s, double* buf, size_t count);
 // host scalars through a small device staging buffer (setup only)
 double allreduce_sum_host(cudaStream_t s, double v);
+// recv (nranks * bytes) <- every rank's send (bytes); device buffers
+void allgather_bytes(cudaStream_t s, const void* send, void* recv, size_t bytes);
+
+// One device block per rank that every other rank can store into (cudaIpc mapping over NVLink): the exchange
+// buffer of the sharded iteration kernel (fadmm_tall.cu).  peer_block is COLLECTIVE: all ranks call it with the
+// same size.  The block and its mappings are kept until the size grows or the communicator goes away.
+struct PeerBlock {
+    bool ok = false;
+    float* local = nullptr;
+    size_t floats = 0;
+    float* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+PeerBlock& peer_block(cudaStream_t s, size_t floats);
+void peer_release();
 
 }  // namespace b200

@@ -24,6 +24,15 @@
 // z and y are triple-buffered and the partial sums double-buffered, which is what makes a
 // single barrier per iteration race-free (a fast CTA can be at most one barrier ahead).
 //
+// Row-sharded runs (one process per GPU, TallPathArgs::nranks > 1): every rank holds the same K^-1 and
+// owns the row range [p r / N, p (r + 1) / N); its CTAs stream only those rows (400 MB / N per iteration:
+// L2-resident from N = 4 on).  The exchange of an iteration is fused into the kernel over NVLink peer
+// memory: the new z / y entries of the own rows and the CTA's six partial sums are stored straight into
+// every peer's state block (cudaIpc-mapped), and the grid barrier becomes a two-level barrier -- the local
+// release / acquire counter, then one system-scope flag per source rank written by CTA 0 into each peer
+// and polled by all CTAs.  Phase [C] reduces the N x G partials in rank-major order, so all ranks compute
+// bit-identical scalars and iterates; no NCCL call and no host round trip inside the lambda path.
+//
 // Mixed precision follows the reference: vectors float, scalars double; double scalars are
 // rounded to float where Eigen would do so (rho * r, adj_y / rho, (1+t) * z), and the prox
 // compares/subtracts in double (ADMMLassoTall.h:64-67).  No FMA contraction is allowed on
@@ -53,6 +62,16 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsig
 {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 // all CTAs of the (co-resident, cooperative) grid
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target)
 {
@@ -64,6 +83,43 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
         __threadfence();
     }
     __syncthreads();
+}
+// All CTAs of all ranks.  Every thread has fenced its peer stores at system scope before the CTA arrives on
+// the local counter; CTA 0 then publishes the barrier number to every peer (release.sys) and every CTA waits
+// until all peers have published theirs (acquire.sys).  A rank can be at most one barrier ahead of another.
+// Bounded wait: a peer that never arrives (lost process) raises *abort instead of hanging the GPU.
+__device__ __forceinline__ bool multi_rank_barrier(const TallPathArgs& a, unsigned long long nbar, int G, float* const* blocks,
+                                                   volatile int* s_abort)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool ok = true;
+        const long long t0 = clock64();
+        const long long limit = 12000000000LL;                         // ~6 s at 2 GHz
+        __threadfence();
+        red_release_add_u64(a.barrier, 1ULL);
+        while (ld_acquire_u64(a.barrier) < nbar * (unsigned long long)G) {
+            if (*(volatile int*)a.abort_flag || clock64() - t0 > limit) { ok = false; break; }
+        }
+        if (ok) {
+            if (blockIdx.x == 0)
+                for (int k = 0; k < a.nranks; k++)
+                    if (k != a.rank) st_release_sys_u64(reinterpret_cast<unsigned long long*>(blocks[k] + a.off_flags) + a.rank, nbar);
+            const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(blocks[a.rank] + a.off_flags);
+            for (int k = 0; k < a.nranks && ok; k++) {
+                if (k == a.rank) continue;
+                while (ld_acquire_sys_u64(mine + k) < nbar) {
+                    if (*(volatile int*)a.abort_flag || clock64() - t0 > limit) { ok = false; break; }
+                }
+            }
+        }
+        if (!ok) atomicExch(a.abort_flag, 1);
+        *s_abort = ok ? 0 : 1;
+        __threadfence();
+    }
+    __syncthreads();
+    return *s_abort == 0;
 }
 
 struct ProxParams {
@@ -106,7 +162,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
     const int p = a.p;
-    const int r0 = min(p, cta * rows_per_cta), r1 = min(p, r0 + rows_per_cta);
+    const int NR = a.nranks > 1 ? a.nranks : 1;
+    const int R0 = NR > 1 ? (int)((long long)p * a.rank / NR) : 0, R1 = NR > 1 ? (int)((long long)p * (a.rank + 1) / NR) : p;
+    const int r0 = min(R1, R0 + cta * rows_per_cta), r1 = min(R1, r0 + rows_per_cta);
+    __shared__ int s_abort;
+    float* blocks[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) blocks[k] = a.peers[k];
     const int nrows = r1 - r0;
     const int ntasks = nrows * TP_SEG;
     const int segv = ((ld / 4) + TP_SEG - 1) / TP_SEG;   // float4 per segment
@@ -116,7 +178,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
     auto yb = [&](int i) -> float* { return a.state + (size_t)(3 + i) * ld; };    // triple-buffered y
     float* adj_z = a.state + 6 * (size_t)ld;
     float* adj_y = a.state + 7 * (size_t)ld;
-    float* partials = a.state + 8 * (size_t)ld;          // [2][G][PART_STRIDE]
+    float* partials = a.state + 8 * (size_t)ld;          // [2][NR * G][PART_STRIDE]
+    const size_t off_z = 0, off_y = 3 * (size_t)ld, off_part = 8 * (size_t)ld;
+    const int NG = NR * G;
 
     const double rho = a.rho;
     const float frho = (float)rho;
@@ -134,7 +198,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
         const ProxParams prox = make_prox(a.enet, lambda, rho, a.alpha);
         const bool tracing = (a.trace != nullptr) && (k == a.trace_lambda);
 
-        // rhs = XY - adj_y + rho * adj_z from the stored extrapolation (cold start: zeros)
+        // rhs = XY - adj_y + rho * adj_z from the stored extrapolation (cold start: zeros).  On a warm start this
+        // is the rhs the last iteration already left in shared memory (the loop exits before a new extrapolation
+        // is formed); a sharded run keeps it there, because it stores adj_* for its own rows only.
+        if (k == 0 || NR == 1)
         for (int v = tid; v < nvec; v += TP_THREADS) {
             const float4 xy = __ldg(reinterpret_cast<const float4*>(a.XY) + v);
             const float4 ay = ldcg4(adj_y + 4 * v), az = ldcg4(adj_z + 4 * v);
@@ -199,6 +266,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
                 const float yn = __fadd_rn(ay, __fmul_rn(frho, res));
                 zb(nxt)[i] = zn;
                 yb(nxt)[i] = yn;
+                if (NR > 1) {
+                    for (int kk = 0; kk < NR; kk++) {
+                        if (kk == a.rank) continue;
+                        blocks[kk][off_z + (size_t)nxt * ld + i] = zn;
+                        blocks[kk][off_y + (size_t)nxt * ld + i] = yn;
+                    }
+                }
                 const float d1 = zn - zo, d2 = zn - az;
                 ps[0] += res * res; ps[1] += d1 * d1; ps[2] += d2 * d2;
                 ps[3] += xv * xv;   ps[4] += zn * zn; ps[5] += yn * yn;
@@ -213,17 +287,21 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
             if (tid < NSUM) {
                 float s = 0.f;
                 for (int w = 0; w < TP_WARPS; w++) s += s_red[w][tid];
-                partials[((size_t)(git & 1u) * G + cta) * PART_STRIDE + tid] = s;
+                const size_t slot = ((size_t)(git & 1u) * NG + (size_t)a.rank * (NR > 1 ? G : 0) + cta) * PART_STRIDE + tid;
+                partials[slot] = s;
+                for (int kk = 0; kk < NR; kk++)
+                    if (NR > 1 && kk != a.rank) blocks[kk][off_part + slot] = s;
             }
 
             nbar++;
-            grid_barrier(a.barrier, nbar * (unsigned long long)G);
+            if (NR == 1) grid_barrier(a.barrier, nbar * (unsigned long long)G);
+            else if (!multi_rank_barrier(a, nbar, G, blocks, &s_abort)) return;
 
             // ---- [C] global scalars, identical in every CTA ----------------------------------------
             if (warp < NSUM) {
                 double s = 0.0;
-                const float* src = partials + (size_t)(git & 1u) * G * PART_STRIDE + warp;
-                for (int c = lane; c < G; c += 32) s += (double)__ldcg(src + (size_t)c * PART_STRIDE);
+                const float* src = partials + (size_t)(git & 1u) * NG * PART_STRIDE + warp;
+                for (int c = lane; c < NG; c += 32) s += (double)__ldcg(src + (size_t)c * PART_STRIDE);
                 s = warp_sum(s);
                 if (lane == 0) s_sum[warp] = s;
             }
@@ -294,9 +372,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
         if (niter == a.maxit + 1) { /* loop ran out: git already advanced by the for-increment */ }
 
         // solution at this lambda = current z (own rows)
-        for (int r = tid; r < nrows; r += TP_THREADS) a.z_out[(size_t)k * p + r0 + r] = __ldcg(zb(cur) + r0 + r);
+        for (int r = tid; r < nrows; r += TP_THREADS) {
+            const float zv = __ldcg(zb(cur) + r0 + r);
+            a.z_out[(size_t)k * p + r0 + r] = zv;
+            for (int kk = 0; kk < NR; kk++)
+                if (NR > 1 && kk != a.rank) blocks[kk][a.off_zout + (size_t)k * p + r0 + r] = zv;
+        }
         if (cta == 0 && tid == 0) a.niter_out[k] = niter;
     }
+    // the peers' rows of z_out have landed in this rank's block once everybody has passed this point
+    if (NR > 1) { nbar++; multi_rank_barrier(a, nbar, G, blocks, &s_abort); }
 }
 
 // stand-alone fused pass over long vectors (HBM-bound when len >> L2)
@@ -370,7 +455,7 @@ __global__ void fused_zu_finish_kernel(const float* __restrict__ part, int nbloc
 size_t tall_state_floats(int p)
 {
     const size_t ld = ((size_t)p + 3) & ~(size_t)3;
-    return 8 * ld + 2 * (size_t)1024 * PART_STRIDE;
+    return 8 * ld + 2 * (size_t)2048 * PART_STRIDE;          // partial slots: up to 8 ranks x 148 CTAs, double-buffered
 }
 
 int launch_tall_path(cudaStream_t s, const TallPathArgs& a)
@@ -379,10 +464,16 @@ int launch_tall_path(cudaStream_t s, const TallPathArgs& a)
     const int ld = (p + 3) & ~3;
     const int sms = sm_count();
     // enough rows per CTA to amortise the barrier; never more CTAs than SMs (co-residency)
-    int G = std::min(sms, std::max(1, (p + 7) / 8));
-    int rows_per_cta = (p + G - 1) / G;
+    // rows of this rank (the kernel uses the same split); every rank must run the SAME G for the partial slots
+    const int NR = a.nranks > 1 ? a.nranks : 1;
+    if (NR > 8) throw ArgError("tall path: at most 8 ranks share one lambda path");
+    int own = 0;
+    for (int r = 0; r < NR; r++) own = std::max(own, (int)((long long)p * (r + 1) / NR) - (int)((long long)p * r / NR));
+    int G = std::min(sms, std::max(1, (own + 7) / 8));
+    int rows_per_cta = (own + G - 1) / G;
     rows_per_cta = (rows_per_cta + 3) & ~3;
-    G = std::min(G, (p + rows_per_cta - 1) / rows_per_cta);
+    G = std::min(G, (own + rows_per_cta - 1) / rows_per_cta);
+    if ((size_t)NR * G > 2048) throw ArgError("tall path: too many partial-sum slots");
     const size_t smem = sizeof(float) * ((size_t)ld + (size_t)rows_per_cta * TP_SEG);
     if (smem > 200 * 1024) throw ArgError("tall path: p too large for the shared-memory resident rhs (p <= 50000)");
     static size_t smem_set = 0;

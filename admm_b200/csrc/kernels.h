@@ -110,6 +110,12 @@ struct TallPathArgs {
     int* trace_rows;        // device int
     unsigned long long* barrier;   // device counter, zeroed
     int snake;              // alternate the row sweep direction every iteration (L2 reuse)
+    // row-sharded runs: state / z_out live in one cudaIpc-exported block per rank, mapped into every peer
+    int nranks = 1, rank = 0;
+    float* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // block base of each rank (peers[rank] == state)
+    size_t off_flags = 0;   // float offset of the 8 x u64 barrier flags inside a block
+    size_t off_zout = 0;    // float offset of z_out inside a block
+    int* abort_flag = nullptr;   // device int (local), zeroed; set when a peer did not arrive in time
 };
 size_t tall_state_floats(int p);
 // returns the grid size used

@@ -376,8 +376,24 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     T.factor = tm.stop();
 
     // ---- the lambda path: one persistent kernel ------------------------------------------------
-    DevBuf<float> state(tall_state_floats((int)p));
-    DevBuf<float> z_out((size_t)nl * (size_t)p);
+    // Row-sharded runs: every rank holds the same K^-1, so the iterations are sharded too -- rank r streams
+    // rows [p r / N, p (r + 1) / N) only and the per-iteration exchange (new z / y entries, partial norms, a
+    // barrier flag) goes through cudaIpc-mapped peer memory inside the kernel (fadmm_tall.cu).  State and
+    // z_out then live in the exported block.  B200ADMM_SHARD_ITER=0 (or a failed mapping) keeps the replicated
+    // iterations.
+    const char* shard_env = getenv("B200ADMM_SHARD_ITER");
+    const size_t state_floats = tall_state_floats((int)p);
+    const size_t off_flags = (state_floats + 3) & ~(size_t)3, off_zout = off_flags + 32;
+    PeerBlock* pb = nullptr;
+    if (cm.active() && cm.nranks <= 8 && !(shard_env && !strcmp(shard_env, "0"))) {
+        PeerBlock& blk = peer_block(s, off_zout + (size_t)nl * (size_t)p);
+        if (blk.ok) pb = &blk;
+    }
+    DevBuf<float> state, z_out;
+    DevBuf<int> abort_dev(1);
+    if (!pb) { state.alloc(state_floats); z_out.alloc((size_t)nl * (size_t)p); }
+    float* const state_p = pb ? pb->local : state.p;
+    float* const z_out_p = pb ? pb->local + off_zout : z_out.p;
     DevBuf<int> niter_dev(nl), trace_rows(1);
     DevBuf<double> lam_dev(nl);
     DevBuf<unsigned long long> barrier(1);
@@ -386,7 +402,15 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     const bool tracing = tr.buf && tr.cap > 0 && tr.which >= 0 && tr.which < nl;
     if (tracing) trace_dev.alloc((size_t)5 * tr.cap);
 
-    state.zero(s);
+    if (pb) {
+        // nobody may store into a peer's block before that peer has cleared it
+        CUDA_CHECK(cudaMemsetAsync(pb->local, 0, off_zout * sizeof(float), s));
+        abort_dev.zero(s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        (void)allreduce_sum_host(s, 0.0);
+    } else {
+        state.zero(s);
+    }
     barrier.zero(s);
     trace_rows.zero(s);
     CUDA_CHECK(cudaMemcpyAsync(lam_dev.p, ilam.data(), nl * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -395,7 +419,12 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     a.Kinv = G.p; a.XY = XY.p; a.lambdas = lam_dev.p; a.nl = nl; a.p = (int)p; a.maxit = rq.opts.maxit;
     a.eps_abs = rq.opts.eps_abs; a.eps_rel = rq.opts.eps_rel; a.rho = rho;
     a.enet = rq.enet ? 1 : 0; a.alpha = rq.alpha;
-    a.state = state.p; a.z_out = z_out.p; a.niter_out = niter_dev.p;
+    a.state = state_p; a.z_out = z_out_p; a.niter_out = niter_dev.p;
+    if (pb) {
+        a.nranks = cm.nranks; a.rank = cm.rank;
+        for (int k = 0; k < cm.nranks; k++) a.peers[k] = pb->peers[k];
+        a.off_flags = off_flags; a.off_zout = off_zout; a.abort_flag = abort_dev.p;
+    }
     a.trace = tracing ? trace_dev.p : nullptr; a.trace_cap = tracing ? tr.cap : 0; a.trace_lambda = tracing ? tr.which : -1;
     a.trace_rows = trace_rows.p; a.barrier = barrier.p;
     const char* snake_env = getenv("B200ADMM_SNAKE");
@@ -410,7 +439,9 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     out->niter = (int*)malloc(sizeof(int) * nl);
     out->lambda = (double*)malloc(sizeof(double) * nl);
     if (!out->niter || !out->lambda) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
-    CUDA_CHECK(cudaMemcpyAsync(z_all.data(), z_out.p, z_all.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(z_all.data(), z_out_p, z_all.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    int aborted = 0;
+    if (pb) CUDA_CHECK(cudaMemcpyAsync(&aborted, abort_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(out->niter, niter_dev.p, nl * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (tracing) {
         int rows = 0;
@@ -421,6 +452,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         if (tr.nrows) *tr.nrows = rows;
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
+    if (aborted) throw CodeError(B200ADMM_ENCCL, "sharded lambda path: a peer rank did not reach the iteration barrier in time");
     for (int k = 0; k < nl; k++) out->lambda[k] = lam[k];
     out->nlambda = nl;
     finish_lasso_path(z_all, nl, p, flag, st.meanX, st.scaleX, st.meanY, st.scaleY, out);
