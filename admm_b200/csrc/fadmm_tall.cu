@@ -84,20 +84,22 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
     }
     __syncthreads();
 }
-// All CTAs of all ranks.  Every thread has fenced its peer stores at system scope before the CTA arrives on
-// the local counter; CTA 0 then publishes the barrier number to every peer (release.sys) and every CTA waits
-// until all peers have published theirs (acquire.sys).  A rank can be at most one barrier ahead of another.
+// All CTAs of all ranks, two levels.  After the CTA-wide sync ONE thread fences at system scope (which orders
+// the peer stores of every thread of the CTA, exactly as in a cooperative grid sync) and arrives on the local
+// counter; when the local grid is complete, CTA 0 publishes the barrier number to every peer (one release.sys
+// store per peer) and every CTA waits until all peers have published theirs (acquire.sys).  Same-address
+// atomics serialise at ~27 cycles each, so the arrivals stay local (G per counter) and only N - 1 words cross
+// NVLink per rank and barrier.  A rank can be at most one barrier ahead of another.
 // Bounded wait: a peer that never arrives (lost process) raises *abort instead of hanging the GPU.
 __device__ __forceinline__ bool multi_rank_barrier(const TallPathArgs& a, unsigned long long nbar, int G, float* const* blocks,
                                                    volatile int* s_abort)
 {
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         bool ok = true;
         const long long t0 = clock64();
         const long long limit = 12000000000LL;                         // ~6 s at 2 GHz
-        __threadfence();
+        __threadfence_system();
         red_release_add_u64(a.barrier, 1ULL);
         while (ld_acquire_u64(a.barrier) < nbar * (unsigned long long)G) {
             if (*(volatile int*)a.abort_flag || clock64() - t0 > limit) { ok = false; break; }
@@ -116,7 +118,6 @@ __device__ __forceinline__ bool multi_rank_barrier(const TallPathArgs& a, unsign
         }
         if (!ok) atomicExch(a.abort_flag, 1);
         *s_abort = ok ? 0 : 1;
-        __threadfence();
     }
     __syncthreads();
     return *s_abort == 0;
