@@ -108,13 +108,21 @@ __device__ __forceinline__ bool multi_rank_barrier(const TallPathArgs& a, unsign
             if (blockIdx.x == 0)
                 for (int k = 0; k < a.nranks; k++)
                     if (k != a.rank) st_release_sys_u64(reinterpret_cast<unsigned long long*>(blocks[k] + a.off_flags) + a.rank, nbar);
+            // poll all peers' flags together (independent relaxed loads: one L2 round trip per sweep, not one per
+            // peer), then a single acquire fence
             const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(blocks[a.rank] + a.off_flags);
-            for (int k = 0; k < a.nranks && ok; k++) {
-                if (k == a.rank) continue;
-                while (ld_acquire_sys_u64(mine + k) < nbar) {
-                    if (*(volatile int*)a.abort_flag || clock64() - t0 > limit) { ok = false; break; }
+            for (;;) {
+                unsigned long long lo = ~0ULL;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    unsigned long long v = ~0ULL;
+                    if (k < a.nranks && k != a.rank) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
+                    lo = v < lo ? v : lo;
                 }
+                if (lo >= nbar) break;
+                if (*(volatile int*)a.abort_flag || clock64() - t0 > limit) { ok = false; break; }
             }
+            __threadfence_system();
         }
         if (!ok) atomicExch(a.abort_flag, 1);
         *s_abort = ok ? 0 : 1;
