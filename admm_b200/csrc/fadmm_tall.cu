@@ -92,7 +92,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 // NVLink per rank and barrier.  A rank can be at most one barrier ahead of another.
 // Bounded wait: a peer that never arrives (lost process) raises *abort instead of hanging the GPU.
 __device__ __forceinline__ bool multi_rank_barrier(const TallPathArgs& a, unsigned long long nbar, int G, float* const* blocks,
-                                                   volatile int* s_abort)
+                                                   volatile int* s_abort, long long* tp = nullptr)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -100,14 +100,21 @@ __device__ __forceinline__ bool multi_rank_barrier(const TallPathArgs& a, unsign
         const long long t0 = clock64();
         const long long limit = 12000000000LL;                         // ~6 s at 2 GHz
         __threadfence_system();
+        if (tp) tp[0] = clock64();
         red_release_add_u64(a.barrier, 1ULL);
         while (ld_acquire_u64(a.barrier) < nbar * (unsigned long long)G) {
             if (*(volatile int*)a.abort_flag || clock64() - t0 > limit) { ok = false; break; }
         }
+        if (tp) tp[1] = clock64();
         if (ok) {
-            if (blockIdx.x == 0)
+            if (blockIdx.x == 0) {
+                // ONE system fence, then relaxed stores: a release store per peer repeats the fence N - 1 times
+                // (measured 3.2 us each -- the peer wait was 10 us at N = 4 and 22 us at N = 8)
+                __threadfence_system();
                 for (int k = 0; k < a.nranks; k++)
-                    if (k != a.rank) st_release_sys_u64(reinterpret_cast<unsigned long long*>(blocks[k] + a.off_flags) + a.rank, nbar);
+                    if (k != a.rank)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(reinterpret_cast<unsigned long long*>(blocks[k] + a.off_flags) + a.rank), "l"(nbar) : "memory");
+            }
             // poll all peers' flags together (independent relaxed loads: one L2 round trip per sweep, not one per
             // peer), then a single acquire fence
             const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(blocks[a.rank] + a.off_flags);
@@ -175,6 +182,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
     const int R0 = NR > 1 ? (int)((long long)p * a.rank / NR) : 0, R1 = NR > 1 ? (int)((long long)p * (a.rank + 1) / NR) : p;
     const int r0 = min(R1, R0 + cta * rows_per_cta), r1 = min(R1, r0 + rows_per_cta);
     __shared__ int s_abort;
+    unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // CTA 0 / thread 0: cycles in [A], [B], fence, local barrier, peer wait, [C] scalars, [C] total; iterations
     float* blocks[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) blocks[k] = a.peers[k];
@@ -226,6 +234,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
         int niter = a.maxit + 1;
         for (int it = 0; it < a.maxit; it++, git++) {
             const int nxt = (cur + 1) % 3;
+            const long long tA0 = clock64();
             // tolerances from the iterate before this step (FADMMBase.h:187-188)
             const double eps_primal = fmax((double)sqrtf((float)sx2), (double)sqrtf((float)sz2)) * a.eps_rel + sqrt_p * a.eps_abs;
             const double eps_dual = (double)sqrtf((float)sy2) * a.eps_rel + sqrt_p * a.eps_abs;
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
             __syncthreads();
 
             // ---- [B] own rows: z, residual, y, partial sums -------------------------------------
+            const long long tB0 = clock64();
             float ps[NSUM] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int r = tid; r < nrows; r += TP_THREADS) {
                 const int i = r0 + r;
@@ -302,9 +312,21 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
                     if (NR > 1 && kk != a.rank) blocks[kk][off_part + slot] = s;
             }
 
+            if (a.prof && cta == 0 && tid == 0) { const long long t = clock64(); pf[0] += (unsigned long long)(tB0 - tA0); pf[1] += (unsigned long long)(t - tB0); }
             nbar++;
             if (NR == 1) grid_barrier(a.barrier, nbar * (unsigned long long)G);
-            else if (!multi_rank_barrier(a, nbar, G, blocks, &s_abort)) return;
+            else {
+                long long tp[2] = {0, 0};
+                const long long tb0 = clock64();
+                if (!multi_rank_barrier(a, nbar, G, blocks, &s_abort, (a.prof && cta == 0) ? tp : nullptr)) return;
+                if (a.prof && cta == 0 && tid == 0) {
+                    const long long tb1 = clock64();
+                    pf[2] += (unsigned long long)(tp[0] - tb0);      // CTA sync + system fence
+                    pf[3] += (unsigned long long)(tp[1] - tp[0]);    // local grid barrier
+                    pf[4] += (unsigned long long)(tb1 - tp[1]);      // flag publication + wait for the peers
+                }
+            }
+            const long long tC0 = clock64();
 
             // ---- [C] global scalars, identical in every CTA ----------------------------------------
             if (warp < NSUM) {
@@ -327,6 +349,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
                 row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
                 *a.trace_rows = it + 1;
             }
+            if (a.prof && cta == 0 && tid == 0) { pf[5] += (unsigned long long)(clock64() - tC0); pf[7] += 1ULL; }
             if (resid_primal < eps_primal && resid_dual < eps_dual) { niter = it + 1; git++; break; }
 
             const double old_c = adj_c;
@@ -377,6 +400,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
                 }
             }
             __syncthreads();
+            if (a.prof && cta == 0 && tid == 0) pf[6] += (unsigned long long)(clock64() - tC0);
         }
         if (niter == a.maxit + 1) { /* loop ran out: git already advanced by the for-increment */ }
 
@@ -391,6 +415,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
     }
     // the peers' rows of z_out have landed in this rank's block once everybody has passed this point
     if (NR > 1) { nbar++; multi_rank_barrier(a, nbar, G, blocks, &s_abort); }
+    if (a.prof && cta == 0 && tid == 0)
+        for (int q = 0; q < 8; q++) a.prof[q] = pf[q];
 }
 
 // stand-alone fused pass over long vectors (HBM-bound when len >> L2)

@@ -116,6 +116,7 @@ struct TallPathArgs {
     size_t off_flags = 0;   // float offset of the 8 x u64 barrier flags inside a block
     size_t off_zout = 0;    // float offset of z_out inside a block
     int* abort_flag = nullptr;   // device int (local), zeroed; set when a peer did not arrive in time
+    unsigned long long* prof = nullptr;   // optional (B200ADMM_PATH_PROF=1): 8 cycle counters of CTA 0, summed over the path
 };
 size_t tall_state_floats(int p);
 // returns the grid size used

@@ -427,6 +427,8 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     }
     a.trace = tracing ? trace_dev.p : nullptr; a.trace_cap = tracing ? tr.cap : 0; a.trace_lambda = tracing ? tr.which : -1;
     a.trace_rows = trace_rows.p; a.barrier = barrier.p;
+    DevBuf<unsigned long long> prof_dev;
+    if (getenv("B200ADMM_PATH_PROF")) { prof_dev.alloc(8); prof_dev.zero(s); a.prof = prof_dev.p; }
     const char* snake_env = getenv("B200ADMM_SNAKE");
     a.snake = snake_env ? atoi(snake_env) : 1;
     tm.start();
@@ -452,6 +454,14 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         if (tr.nrows) *tr.nrows = rows;
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
+    if (prof_dev.p) {
+        unsigned long long h[8];
+        CUDA_CHECK(cudaMemcpy(h, prof_dev.p, sizeof h, cudaMemcpyDeviceToHost));
+        const double it = (double)std::max<unsigned long long>(1, h[7]);
+        fprintf(stderr, "[b200admm path profile, rank %d, CTA 0] cycles / iteration: A %.0f  B %.0f  sync+fence %.0f  local barrier %.0f  "
+                        "peer wait %.0f  C scalars %.0f  C total %.0f  (%llu iterations)\n", cm.rank, h[0] / it, h[1] / it, h[2] / it, h[3] / it,
+                h[4] / it, h[5] / it, h[6] / it, h[7]);
+    }
     if (aborted) throw CodeError(B200ADMM_ENCCL, "sharded lambda path: a peer rank did not reach the iteration barrier in time");
     for (int k = 0; k < nl; k++) out->lambda[k] = lam[k];
     out->nlambda = nl;
