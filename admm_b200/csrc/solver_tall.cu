@@ -181,7 +181,10 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     StdStats st;
     const bool host_input = d->dtype == B200ADMM_F32_HOST || d->dtype == B200ADMM_F64_HOST;
     const char* pipe_env = getenv("B200ADMM_PIPELINE");
-    const bool pipelined = host_input && !cm.active() && want_tensor && p >= 1024 && !(pipe_env && !strcmp(pipe_env, "0"));
+    // (row-sharded runs pipeline too: every rank copies its own rows over its own PCIe link; the per-panel
+    // all-reduces of the column statistics need the same panel schedule on every rank, so the panel width is
+    // derived from the global row count)
+    const bool pipelined = host_input && want_tensor && p >= 1024 && !(pipe_env && !strcmp(pipe_env, "0"));
 
     if (pipelined) {
         // ---- host input: copy, DataStd, X'y and the Gram matrix pipelined over column panels --------------
@@ -195,7 +198,8 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         ingest_f32(s, d->y, d->dtype, (size_t)n_local, ys.p);
         standardize_y_sharded(s, ys.p, n_local, n, flag, st);
         const size_t esz = d->dtype == B200ADMM_F64_HOST ? 8 : 4;
-        i64 pw = (i64)(((size_t)3 << 30) / ((size_t)n_local * esz));          // ~3 GB of host data per panel
+        const i64 n_sched = cm.active() ? (n + cm.nranks - 1) / cm.nranks : n_local;
+        i64 pw = (i64)(((size_t)3 << 30) / ((size_t)n_sched * esz));          // ~3 GB of host data per panel
         if (const char* pw_env = getenv("B200ADMM_PANEL_COLS")) pw = atoll(pw_env);     // tests: force several panels
         pw = std::max<i64>(256, (pw / 256) * 256);                        // whole 256-column row blocks of the pair kernel
         // Panel schedule: wide panels first; the last ~1000 columns in single 256-column row blocks.  Whatever
@@ -257,6 +261,8 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
             if (!ok) throw CudaError("pipelined Gram: tensor kernel declined the shape");
         }
         if (use_f16 && gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
+        allreduce_sum(s, XY.p, p);
+        allreduce_sum(s, G.p, (size_t)p * (size_t)ld);
         fetch_std_stats(s, p, flag, d_meanX.p, d_scaleX.p, st);
         T.gram = tm.stop();                                   // copy + DataStd + X'y + Gram, overlapped
         CUDA_CHECK(cudaStreamSynchronize(cs));

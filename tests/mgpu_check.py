@@ -39,7 +39,24 @@ def main():
     lam_c = [0.3, 0.1]
     ref_c = admm_b200.admm_lasso(x, y).penalty(lam_c).parallel(world).opts(maxit=4000).fit()
 
+    # a problem wide enough for the pipelined host ingest (p >= 1024), forced into several column panels
+    os.environ["B200ADMM_PANEL_COLS"] = "256"
+    n2, p2 = 4003, 1100
+    x2 = np.asfortranarray(rng.normal(0.2, 2.0, size=(n2, p2)).astype(np.float32))
+    b2 = np.zeros(p2); b2[:12] = rng.uniform(0.5, 1.5, size=12)
+    y2 = (0.5 + x2 @ b2 + rng.normal(size=n2)).astype(np.float32)
+    q0, qn = D.row_block(n2, world, rank)
+    x2s, y2s = np.asfortranarray(x2[q0:q0 + qn]), y2[q0:q0 + qn].copy()
+    ref2 = admm_b200.admm_lasso(x2, y2).penalty(nlambda=8).fit()
+
     D.init_comm()
+    f2 = admm_b200.admm_lasso(x2s, y2s).penalty(nlambda=8).fit()          # pipelined copy + per-panel all-reduces + sharded iterations
+    b2g, b2r = np.asarray(f2.beta.todense()), np.asarray(ref2.beta.todense())
+    tol2 = max(2e-4, 2e-5 * np.sqrt(p2))
+    assert np.abs(b2g - b2r).max() < tol2, np.abs(b2g - b2r).max()
+    assert abs(int(f2.niter.sum()) - int(ref2.niter.sum())) <= max(3, 0.03 * int(ref2.niter.sum())), (f2.niter, ref2.niter)
+    del os.environ["B200ADMM_PANEL_COLS"]
+
     f = admm_b200.admm_lasso(xs, ys).penalty(nlambda=15).fit()
     bg, br = np.asarray(f.beta.todense()), np.asarray(ref.beta.todense())
     assert np.allclose(f.lambda_, ref.lambda_, rtol=1e-6), (f.lambda_[:3], ref.lambda_[:3])
