@@ -16,8 +16,11 @@
 //   z step                            :  Ax = sum over support columns (row-parallel, fixed chunk order),
 //                                        fused with z = (y_dat + u + rho Ax)/(-1-rho), r = Ax + z, u += rho r
 //                                        and the five squared norms the stopping rule needs.
-// The loop is driven from the host (the support size is data dependent): one small
-// device->host read per iteration.  Compiled with --fmad=false (unfused, reference order).
+// The loop is driven from the host (the support size is data dependent) with ONE small device->host read per
+// iteration (the five norms + the new support size); the z step sizes its launches from the previous support
+// size (an upper bound during active-set steps) and reads the exact count on the device.  The solution of each
+// lambda leaves the device as (index, value) pairs of its support, never as a dense p-vector.
+// Compiled with --fmad=false (unfused, reference order).
 #include "solvers.h"
 #include "kernels.h"
 #include <cmath>
@@ -160,11 +163,21 @@ __global__ void __launch_bounds__(1024) compact_scatter_kernel(const int* __rest
 
 // ---- z step ----------------------------------------------------------------------------------------
 // partial Ax over a chunk of the support: part[chunk][i] = sum_k X(i, supp_k) * x[supp_k]
-__global__ void __launch_bounds__(WT) wide_ax_kernel(const float* __restrict__ X, i64 ldx, i64 n, const int* __restrict__ supp, int nnz,
-                                                     const float* __restrict__ x, int per_chunk, float* __restrict__ part)
+// chunking of the support for the partial Ax sums (the same on host and device)
+__host__ __device__ __forceinline__ int wide_chunks(int nnz, int max_chunks)
+{
+    return nnz > 0 ? max(1, min(max_chunks, (nnz + 255) / 256)) : 0;
+}
+__global__ void __launch_bounds__(WT) wide_ax_kernel(const float* __restrict__ X, i64 ldx, i64 n, const int* __restrict__ supp,
+                                                     const int* __restrict__ nnz_dev, int max_chunks,
+                                                     const float* __restrict__ x, float* __restrict__ part)
 {
     __shared__ int sj[WT];
     __shared__ float sv[WT];
+    const int nnz = *nnz_dev;                             // exact; the grid was sized from an upper bound
+    const int chunks = wide_chunks(nnz, max_chunks);
+    if ((int)blockIdx.y >= chunks) return;
+    const int per_chunk = (nnz + chunks - 1) / chunks;
     const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
     const int k0 = blockIdx.y * per_chunk, k1 = min(nnz, k0 + per_chunk);
     float acc = 0.f;
@@ -187,10 +200,12 @@ __global__ void __launch_bounds__(WT) wide_ax_kernel(const float* __restrict__ X
 }
 
 // Ax = sum of chunks (fixed order); z = (ydat + y + frho Ax) / den; r = Ax + z; y += frho r; norms
-__global__ void __launch_bounds__(WT) wide_zstep_kernel(const float* __restrict__ part, int chunks, i64 n, const float* __restrict__ ydat,
+__global__ void __launch_bounds__(WT) wide_zstep_kernel(const float* __restrict__ part, const int* __restrict__ nnz_dev, int max_chunks, i64 n,
+                                                        const float* __restrict__ ydat,
                                                         float frho, float den, float* __restrict__ Ax, float* __restrict__ z,
                                                         float* __restrict__ y, float* __restrict__ psums)
 {
+    const int chunks = wide_chunks(*nnz_dev, max_chunks);
     const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
     float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (i < n) {
@@ -228,6 +243,49 @@ __global__ void wide_finish_sums_kernel(const float* __restrict__ psums, int nbl
         s = warp_sum(s);
         if (lane == 0) out6[q] = s;
     } else if (q == 5 && lane == 0) out6[5] = (double)*nnz;
+}
+
+// vals[i] = x[supp[i]]: the solution of one lambda as (index, value) pairs
+__global__ void __launch_bounds__(WT) wide_gather_kernel(const float* __restrict__ x, const int* __restrict__ supp, int nnz, float* __restrict__ vals)
+{
+    const int i = blockIdx.x * WT + threadIdx.x;
+    if (i < nnz) vals[i] = x[supp[i]];
+}
+
+// DataStd::recover + dgCMatrix assembly from per-lambda support lists (the sparse twin of finish_lasso_path:
+// same arithmetic on the stored entries in index order, /root/reference/src/DataStd.h:183-207, Lasso.cpp:22-30)
+void finish_sparse_path(std::vector<std::vector<int>>& idx, std::vector<std::vector<float>>& val, int nl, i64 p, int flag,
+                        const std::vector<float>& meanX, const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out)
+{
+    std::vector<float> beta0(nl, 0.f);
+    size_t nnz = 0;
+    for (int k = 0; k < nl; k++) {
+        float s = 0.f;
+        for (size_t e = 0; e < idx[k].size(); e++) {
+            const int j = idx[k][e];
+            float c = val[k][e];
+            if (flag == 1 || flag == 3) c /= scaleX[j];
+            if (flag != 0) c *= scaleY;
+            if (flag == 2 || flag == 3) s += c * meanX[j];
+            val[k][e] = c;
+            if (c != 0.f) nnz++;
+        }
+        if (flag == 2 || flag == 3) beta0[k] = meanY - s;
+        nnz++;                                              // the intercept row is always stored
+    }
+    out->colptr = (int64_t*)malloc(sizeof(int64_t) * (nl + 1));
+    out->rowidx = (int*)malloc(sizeof(int) * std::max<size_t>(nnz, 1));
+    out->val = (double*)malloc(sizeof(double) * std::max<size_t>(nnz, 1));
+    if (!out->colptr || !out->rowidx || !out->val) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
+    size_t pos = 0;
+    for (int k = 0; k < nl; k++) {
+        out->colptr[k] = (int64_t)pos;
+        out->rowidx[pos] = 0; out->val[pos] = (double)beta0[k]; pos++;
+        for (size_t e = 0; e < idx[k].size(); e++)
+            if (val[k][e] != 0.f) { out->rowidx[pos] = idx[k][e] + 1; out->val[pos] = (double)val[k][e]; pos++; }
+    }
+    out->colptr[nl] = (int64_t)pos;
+    out->nrow = p + 1;
 }
 
 inline bool is_regular_update(unsigned c)
@@ -382,7 +440,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     DevBuf<double> sums6(6);
     int max_chunks = 64;
     DevBuf<float> part((size_t)max_chunks * (size_t)n);
-    int cur_supp = 0, nnz = 0;
+    int cur_supp = 0, nnz = 0, nnz_bound = 0;
 
     auto compact = [&](const int* src, int len, int* dst) {
         const int nb = (len + 1023) / 1024;
@@ -393,7 +451,8 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     };
 
     TraceRequest& tr = trace_request();
-    std::vector<float> x_all((size_t)nl * (size_t)p);
+    std::vector<std::vector<int>> idx_all(nl);
+    std::vector<std::vector<float>> val_all(nl);
     out->niter = (int*)malloc(sizeof(int) * nl);
     out->lambda = (double*)malloc(sizeof(double) * nl);
     if (!out->niter || !out->lambda) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
@@ -419,6 +478,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             // ---------------- x step ----------------
             if (!rq.enet && (double)lambda > (double)lambda0 - 1e-5) {
                 if (nnz > 0) { x.zero(s); nnz = 0; CUDA_CHECK(cudaMemsetAsync(nnz_dev.p, 0, sizeof(int), s)); }
+                nnz_bound = 0;
             } else {
                 WideProx q;
                 q.enet = rq.enet ? 1 : 0;
@@ -444,18 +504,17 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                     }
                 }
                 iter_counter++;
-                CUDA_CHECK(cudaMemcpyAsync(&nnz, nnz_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-                CUDA_CHECK(cudaStreamSynchronize(s));
+                // the new support size stays on the device: a regular step can grow the support to anything up to p,
+                // an active-set step can only shrink it
+                nnz_bound = regular ? (int)std::min<i64>(p, 2147483647LL) : nnz;
             }
             // ---------------- z step, residual, dual update ----------------
-            int chunks = std::max(1, std::min(max_chunks, (nnz + 255) / 256));
-            const int per_chunk = nnz > 0 ? (nnz + chunks - 1) / chunks : 0;
-            if (nnz == 0) chunks = 0;
-            if (chunks > 0) {
-                wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks), WT, 0, s>>>(X, ldx, n, supp[cur_supp].p, nnz, x.p, per_chunk, part.p);
+            const int chunks_bound = wide_chunks(nnz_bound, max_chunks);
+            if (chunks_bound > 0) {
+                wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks_bound), WT, 0, s>>>(X, ldx, n, supp[cur_supp].p, nnz_dev.p, max_chunks, x.p, part.p);
                 KERNEL_CHECK();
             }
-            wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, chunks, n, ydat.p, frho, (float)(-1 - rho), Ax.p, z.p, y.p, psums.p); KERNEL_CHECK();
+            wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, frho, (float)(-1 - rho), Ax.p, z.p, y.p, psums.p); KERNEL_CHECK();
             wide_finish_sums_kernel<<<1, 192, 0, s>>>(psums.p, zblocks, nnz_dev.p, sums6.p); KERNEL_CHECK();
             double h[6];
             CUDA_CHECK(cudaMemcpyAsync(h, sums6.p, sizeof h, cudaMemcpyDeviceToHost, s));
@@ -463,6 +522,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             const double resid_dual = rho * (double)sqrt_sprad * (double)std::sqrt((float)h[0]);
             const double resid_primal = (double)std::sqrt((float)h[1]);
             sAx2 = h[2]; sz2 = h[3]; sy2 = h[4];
+            nnz = (int)h[5];                                               // exact support size after this iteration's x step
             if (tracing && i < tr.cap) {
                 double* row = tr.buf + 5 * (size_t)i;
                 row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
@@ -473,14 +533,21 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
         }
         out->niter[k] = i + 1;
         out->lambda[k] = lam[k];
-        CUDA_CHECK(cudaMemcpyAsync(x_all.data() + (size_t)k * p, x.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+        // solution of this lambda: support indices + values (supp[cur_supp] lists exactly the non-zeros of x)
+        idx_all[k].resize(nnz); val_all[k].resize(nnz);
+        if (nnz > 0) {
+            wide_gather_kernel<<<(nnz + WT - 1) / WT, WT, 0, s>>>(x.p, supp[cur_supp].p, nnz, vec.p); KERNEL_CHECK();
+            CUDA_CHECK(cudaMemcpyAsync(idx_all[k].data(), supp[cur_supp].p, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(val_all[k].data(), vec.p, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));      // vec / supp are rewritten by the next lambda's first step
+        }
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
     T.iterate = tm.stop();
 
     tm.start();
     out->nlambda = nl;
-    finish_lasso_path(x_all, nl, p, flag, meanX, scaleX, meanY, scaleY, out);
+    finish_sparse_path(idx_all, val_all, nl, p, flag, meanX, scaleX, meanY, scaleY, out);
     T.finish = tm.stop();
     T.total = wall_now() - t_begin;
     out->rho = rho; out->eig = sprad; out->lambda0 = lambda0; out->t = T;
