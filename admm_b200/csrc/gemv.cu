@@ -89,14 +89,49 @@ __global__ void __launch_bounds__(256) gemv_t_block_kernel(const T* __restrict__
     }
 }
 
+// long columns cut into nseg row segments: one CTA per (column, segment), partial sums added in segment order
+template <class T>
+__global__ void __launch_bounds__(256) gemv_t_seg_kernel(const T* __restrict__ A, i64 m, i64 lda, const T* __restrict__ v,
+                                                         int nseg, i64 seg_len, T* __restrict__ partial)
+{
+    __shared__ T scratch[33];
+    const i64 j = blockIdx.x / nseg;
+    const int seg = (int)(blockIdx.x % nseg);
+    const i64 r0 = seg * seg_len, r1 = min(m, r0 + seg_len);
+    T s = r1 > r0 ? strided_dot(A + j * lda + r0, v + r0, r1 - r0, (int)threadIdx.x, (int)blockDim.x) : T(0);
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+template <class T>
+__global__ void __launch_bounds__(256) gemv_t_seg_finish_kernel(const T* __restrict__ partial, i64 ncol, int nseg, T* __restrict__ out)
+{
+    const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncol) return;
+    T s = partial[j * nseg];
+    for (int q = 1; q < nseg; q++) s += partial[j * nseg + q];
+    out[j] = s;
+}
+
 template <class T>
 void gemv_t(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T* out)
 {
     if (ncol <= 0) return;
     const int sms = sm_count();
     if (m >= 32768) {
-        // one CTA per column, scheduled dynamically by the hardware (a grid-stride loop over a few
-        // resident CTAs quantises the tail: 5000 columns over 1184 CTAs leave the last round 22 % full)
+        // One CTA per column leaves the last wave of resident CTAs mostly empty (5000 columns over 8 x 148 slots:
+        // 4.2 waves cost 5; LAD's X'v ran at 67 % of the HBM rate).  Columns are therefore cut into row segments
+        // until there are ~16 waves of CTAs; the segment sums are added in segment order (deterministic).
+        const i64 slots = (i64)sms * 8;
+        const int nseg = (int)std::max<i64>(1, std::min<i64>(8, (16 * slots + ncol - 1) / ncol));
+        if (nseg > 1 && ncol * nseg < ((i64)1 << 30)) {
+            const i64 seg_len = (((m + nseg - 1) / nseg) + 3) & ~(i64)3;
+            DevBuf<T> partial((size_t)ncol * nseg);
+            gemv_t_seg_kernel<T><<<(unsigned)(ncol * nseg), 256, 0, s>>>(A, m, lda, v, nseg, seg_len, partial.p);
+            KERNEL_CHECK();
+            gemv_t_seg_finish_kernel<T><<<(unsigned)((ncol + 255) / 256), 256, 0, s>>>(partial.p, ncol, nseg, out);
+            KERNEL_CHECK();
+            return;      // (the block cache keeps `partial` alive for the stream-ordered kernels above)
+        }
         const i64 grid = std::min<i64>(ncol, (i64)1 << 20);
         gemv_t_block_kernel<T><<<(unsigned)grid, 256, 0, s>>>(A, m, ncol, lda, v, out);
     } else {
