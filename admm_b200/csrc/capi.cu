@@ -598,6 +598,25 @@ int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g, int use_te
     });
 }
 
+int b200admm_k_gram_plan(int ntiles, int npairs, int nk, int* cover, long long* per_pair, int* nslices, int* split_tiles)
+{
+    return fenced([&] {
+        if (ntiles < 1 || npairs < 1 || nk < 1 || !cover || !per_pair) throw ArgError("gram plan: bad arguments");
+        gram_f16_plan(ntiles, npairs, nk, cover, per_pair, nslices, split_tiles);
+    });
+}
+
+int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int cap)
+{
+    try {
+        if (p < 1 || !begin || cap < 2) return -1;
+        const std::vector<i64> b = host_panel_schedule(p, panel_cols);
+        if ((int)b.size() > cap) return -1;
+        for (size_t i = 0; i < b.size(); i++) begin[i] = b[i];
+        return (int)b.size() - 1;
+    } catch (...) { return -1; }
+}
+
 int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v, void* out)
 {
     return fenced([&] {

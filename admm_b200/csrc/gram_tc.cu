@@ -846,7 +846,7 @@ __host__ __device__ __forceinline__ HWork h_work(int ntiles, int npairs, int nk)
 }
 struct HItem { int tile, s0, s1, split, tt; };
 // item `i` of pair `pair`: i < rounds are whole tiles; i == rounds is the pair's share of the tail (if any)
-__device__ __forceinline__ bool h_item(const HWork& w, int pair, int i, HItem& it)
+__host__ __device__ __forceinline__ bool h_item(const HWork& w, int pair, int i, HItem& it)
 {
     if (i < w.rounds) { it.tile = pair + i * w.npairs; it.s0 = 0; it.s1 = w.nslices; it.split = 0; it.tt = 0; return true; }
     if (i > w.rounds || w.tail == 0) return false;
@@ -862,7 +862,7 @@ __device__ __forceinline__ bool h_item(const HWork& w, int pair, int i, HItem& i
     it.s1 = (int)((long long)(sl + 1) * w.nslices / w.per_tile);
     return it.s1 > it.s0;
 }
-__device__ __forceinline__ int h_slice_chunk0(const HWork& w, int s) { return (int)((long long)s * w.nch / w.nslices); }
+__host__ __device__ __forceinline__ int h_slice_chunk0(const HWork& w, int s) { return (int)((long long)s * w.nch / w.nslices); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H_THREADS, 1)
 gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles,
@@ -1143,6 +1143,27 @@ bool gram_f16_overflowed(cudaStream_t s)
     CUDA_CHECK(cudaStreamSynchronize(s));
     if (h) CUDA_CHECK(cudaMemsetAsync(overflow_flag(), 0, sizeof(int), s));
     return h != 0;
+}
+
+// Host-side replay of the kernel's work distribution (the same h_work / h_item the device uses): for every
+// (tile, 32-row stage) the number of CTA pairs that compute it goes to cover[tile * nk + ks]; per_pair[q] = stages
+// of pair q.  Unit tests check that every stage of every tile is computed exactly once and that the pairs are
+// balanced, without a GPU.
+void gram_f16_plan(int ntiles, int npairs, int nk, int* cover, long long* per_pair, int* nslices, int* split_tiles)
+{
+    const HWork w = h_work(ntiles, npairs, nk);
+    if (nslices) *nslices = w.nslices;
+    if (split_tiles) *split_tiles = w.per_tile > 1 ? w.tail : 0;
+    for (int q = 0; q < npairs; q++) {
+        long long stages = 0;
+        HItem it;
+        for (int i = 0; h_item(w, q, i, it); i++) {
+            const int ks0 = h_slice_chunk0(w, it.s0) * CHUNK_STEPS, ks1 = std::min(nk, h_slice_chunk0(w, it.s1) * CHUNK_STEPS);
+            for (int ks = ks0; ks < ks1; ks++) cover[(size_t)it.tile * nk + ks]++;
+            stages += ks1 - ks0;
+        }
+        per_pair[q] = stages;
+    }
 }
 
 bool gram_f16_usable(i64 n, i64 p)

@@ -37,6 +37,7 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
 //                            32-row boxes of 16 KB, one TMA burst each); col_begin % 128 == 0
 //   gram_tn_f16_blocked    : same contract as gram_tn_tensor, operands read from Xb (columns < col_end split)
 bool gram_f16_usable(i64 n, i64 p);
+void gram_f16_plan(int ntiles, int npairs, int nk, int* cover, long long* per_pair, int* nslices, int* split_tiles);
 size_t gram_f16_blocked_bytes(i64 n, i64 p);
 void gram_split_f16_blocked(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, i64 col_begin, i64 col_end, void* Xb);
 // DataStd flag 3 fused with the split: reads the RAW columns [col_begin, col_end) of X once, applies

@@ -123,6 +123,21 @@ void standardize_all(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out,
     fetch_std_stats(s, p, flag, d_meanX, d_scaleX, st);
 }
 
+// column panels of the pipelined host ingest: begin[0] = 0 < begin[1] < ... < begin[npan] = p, every boundary but
+// the last a multiple of 256 (whole row blocks of the CTA-pair Gram kernel); pw = width of the wide panels
+std::vector<i64> host_panel_schedule(i64 p, i64 pw)
+{
+    pw = std::max<i64>(256, (pw / 256) * 256);
+    std::vector<i64> b;
+    for (i64 c = 0; c < p;) {
+        b.push_back(c);
+        const i64 left = p - c;
+        c += (left > pw + 768 || pw <= 256) ? std::min(pw, left) : std::min<i64>(256, left);
+    }
+    b.push_back(p);
+    return b;
+}
+
 void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
                        const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out)
 {
@@ -206,13 +221,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         // Gram work belongs to the final panel starts only after the copy has ended (its share of the whole
         // is 2 w / p for a panel of w columns), and a 256-column launch is no longer wasteful: its <= 40 tiles
         // are cut along K over all CTA pairs.
-        std::vector<i64> pan_begin;
-        for (i64 c = 0; c < p;) {
-            pan_begin.push_back(c);
-            const i64 left = p - c;
-            c += (left > pw + 768 || pw <= 256) ? std::min(pw, left) : std::min<i64>(256, left);
-        }
-        pan_begin.push_back(p);
+        const std::vector<i64> pan_begin = host_panel_schedule(p, pw);
         const int npan = (int)pan_begin.size() - 1;
         DevBuf<float> tmp(2 * pw + 8);
         if (use_f16) xty_work.alloc(gram_f16_xty_work_floats(n_local, pw));

@@ -45,6 +45,7 @@ void assemble_csc(const std::vector<std::vector<T>>& cols, const std::vector<T>&
                   i64 p, b200admm_path* out);
 template <class T>
 T recover_sparse(int flag, std::vector<T>& coef, const std::vector<T>& meanX, const std::vector<T>& scaleX, T meanY, T scaleY);
+std::vector<i64> host_panel_schedule(i64 p, i64 pw);
 void ingest_f32(cudaStream_t s, const void* src, int dtype, size_t count, float* dst);
 void ingest_f64(cudaStream_t s, const void* src, int dtype, size_t count, double* dst);
 void add_to_diagonal(cudaStream_t s, float* A, i64 ld, i64 p, float v);

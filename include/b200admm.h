@@ -179,6 +179,13 @@ int b200admm_k_standardize_f32(const void* x_in, void* x_out, void* y_inout, int
  * round-to-nearest split (any fp32 data), 3 tcgen05 3xFP16 hi/lo split (unit-scale columns only, i.e. data
  * standardised by DataStd -- what the solvers use there; values beyond the fp16 range are an error here) */
 int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g /* p x p, full */, int use_tensor);
+/* Host-only planners (no device needed; unit-tested on CPU): the work distribution of the fp16 Gram kernel --
+ * cover[tile * nk + stage] = number of CTA pairs computing that 32-row stage of that 256 x 256 tile (must be 1
+ * everywhere), per_pair[q] = stages handled by pair q, *nslices = canonical K-slices per tile, *split_tiles =
+ * tiles of the last round that are cut along K -- and the column panels of the pipelined host ingest
+ * (returns the number of panels, begin[0 .. npanels] their first columns; -1 on bad arguments). */
+int b200admm_k_gram_plan(int ntiles, int npairs, int nk, int* cover, long long* per_pair, int* nslices, int* split_tiles);
+int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int cap);
 int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v, void* out);
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host);                 /* lower, in place */
 int b200admm_k_spd_inverse_f32(void* a, int64_t p, void* work, int* info_host); /* a <- a^-1 (full) */

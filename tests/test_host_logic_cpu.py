@@ -1,0 +1,84 @@
+"""Host-side scheduling logic of the CUDA library, exercised on CPU through the C ABI's host-only planners
+(no device call): the work distribution of the fp16 CTA-pair Gram kernel (full rounds of whole tiles, the last
+round cut along K into canonical slices) and the column panels of the pipelined host ingest."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def L():
+    from admm_b200 import build, _capi
+    build.build()
+    return _capi.lib()
+
+
+def plan(L, ntiles, npairs, nk):
+    cover = np.zeros(ntiles * nk, dtype=np.int32)
+    per_pair = np.zeros(npairs, dtype=np.int64)
+    ns, st = C.c_int(0), C.c_int(0)
+    rc = L.b200admm_k_gram_plan(ntiles, npairs, nk, cover.ctypes.data, per_pair.ctypes.data, C.byref(ns), C.byref(st))
+    assert rc == 0
+    return cover.reshape(ntiles, nk), per_pair, ns.value, st.value
+
+
+@pytest.mark.parametrize("ntiles,npairs,nk", [
+    (820, 74, 3125),      # the headline shape (p = 1e4: 40 row blocks), shortened K
+    (136, 74, 625), (153, 74, 625), (210, 74, 100),
+    (1, 74, 128), (3, 74, 32), (40, 74, 1000), (74, 74, 7), (75, 74, 5), (820, 74, 1), (6, 74, 3), (37, 74, 97),
+    (5, 2, 50), (7, 1, 9),
+])
+def test_gram_plan_covers_every_stage_exactly_once(L, ntiles, npairs, nk):
+    cover, per_pair, nslices, split_tiles = plan(L, ntiles, npairs, nk)
+    assert (cover == 1).all(), "a (tile, stage) is computed %d times" % int(cover.max() if cover.max() != 1 else cover.min())
+    assert int(per_pair.sum()) == ntiles * nk
+    nch = (nk + 3) // 4
+    assert nslices == min(24, nch)
+    rounds, tail = divmod(ntiles, npairs)
+    assert per_pair.min() >= rounds * nk
+    if tail == 0:
+        assert (per_pair == rounds * nk).all()
+    else:
+        per_tile = npairs // tail
+        assert split_tiles == (tail if per_tile > 1 else 0)
+        # a pair's share of the tail: at most ceil(nslices / per_tile) slices of at most ceil(nch / nslices) chunks
+        worst = -(-nslices // max(per_tile, 1)) * -(-nch // nslices) * 4
+        assert per_pair.max() <= rounds * nk + min(nk, worst)
+
+
+def test_gram_plan_tail_is_spread_over_the_idle_pairs(L):
+    # 820 tiles on 74 pairs: 11 full rounds + 6 tail tiles, each cut over 12 pairs (2 of 24 slices each)
+    nk = 31250
+    _, per_pair, nslices, split_tiles = plan(L, 820, 74, nk)
+    assert nslices == 24 and split_tiles == 6
+    busy = per_pair[per_pair > 11 * nk]
+    assert len(busy) == 72
+    assert busy.max() - 11 * nk <= nk // 12 + 8
+    # the whole launch costs 11.09 tile-times instead of 12
+    assert per_pair.max() / nk < 11.1
+
+
+def schedule(L, p, pw):
+    buf = np.zeros(4096, dtype=np.int64)
+    npan = L.b200admm_k_panel_schedule(p, pw, buf.ctypes.data, len(buf))
+    assert npan >= 1
+    return buf[: npan + 1]
+
+
+@pytest.mark.parametrize("p,pw", [(10000, 768), (10000, 256), (1100, 256), (1024, 768), (80000, 6000), (4352, 1000), (300, 768), (257, 100)])
+def test_panel_schedule(L, p, pw):
+    b = schedule(L, p, pw)
+    assert b[0] == 0 and b[-1] == p
+    assert (np.diff(b) > 0).all()
+    assert (b[1:-1] % 256 == 0).all()                      # every interior boundary is a whole 256-column row block
+    w = max(256, pw // 256 * 256)
+    assert np.diff(b).max() <= w
+    if p > w + 768:
+        assert np.diff(b)[-1] <= 256 and np.diff(b)[-2] <= 256      # the tail of the copy is followed by little Gram work
+
+
+def test_panel_schedule_rejects_bad_arguments(L):
+    buf = np.zeros(4, dtype=np.int64)
+    assert L.b200admm_k_panel_schedule(0, 256, buf.ctypes.data, 4) == -1
+    assert L.b200admm_k_panel_schedule(100000, 256, buf.ctypes.data, 4) == -1      # not enough room
