@@ -4,21 +4,31 @@
 // (/root/reference/src/Linalg/BlasWrapper.h:73-112, called from src/ADMMLassoTall.h:191-192):
 // 2 n p^2 / 2 flops, 93 % of the whole lambda-path wall time when done on the CUDA cores.
 //
-// The reference computes the Gram matrix in float32 (Eigen GEMM).  A single TF32 pass would
-// perturb X'X at the 1e-3 level, far outside the parity band, so every product is split
-//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
-//                   lo = x - hi (exact in fp32; |lo| < 2^-10 |x|)
+// The reference computes the Gram matrix in float32 (Eigen GEMM).  A single low-precision pass would
+// perturb X'X at the 1e-3 level, far outside the parity band, so every operand is split
+//     x = hi + lo          (hi: the leading 11 significant bits, lo: the next 11)
 //     a b ~= hi_a hi_b + lo_a hi_b + hi_a lo_b            (dropped lo_a lo_b < 2^-20 |a b|)
-// i.e. three tcgen05.mma.kind::tf32 per k-slice with fp32 accumulation in TMEM.  The tensor
-// core adds into its accumulator with truncation (measured: a relative bias of about -5e-8 per
-// accumulating MMA on all-positive sums), so long accumulations are cut into chunks of 128 rows:
-// each chunk is accumulated in TMEM from zero (48 MMAs) and then added, with round-to-nearest fp32
-// adds on the CUDA cores, to per-thread register accumulators that live for the whole tile.
+// i.e. three tensor-core products per k-slice with fp32 accumulation in TMEM.  The tensor core adds into
+// its accumulator with truncation (measured: a relative bias of about -5e-8 per accumulating MMA on
+// all-positive sums), so long accumulations are cut into chunks of 128 rows: each chunk is accumulated in
+// TMEM from zero and then added, with round-to-nearest fp32 adds on the CUDA cores, to per-thread register
+// accumulators.
 //
-// Kernel anatomy (one persistent CTA per SM, 512 threads, tile = 128 x 192 of G, k-slice = 32):
+// Three kernels, one per regime (host entry points at the end of the file):
+//   gram_pair_h_kernel   standardised data (DataStd flag 3, |x| <= sqrt(n)), p >= 256: operands PRE-SPLIT once
+//                        into fp16 hi | lo halves in a tile-blocked array (split_f16_blocked_kernel, or fused
+//                        with DataStd's apply step and X'y in std_split_xty_kernel), tcgen05 kind::f16,
+//                        CTA pairs on 256 x 256 tiles, canonical K-slices with a K-split last round.
+//                        The headline path: 330-345 TFLOP/s of SYRK flops at n = 1e6, p = 1e4.
+//   gram_pair_kernel     any fp32 data, p >= 256: kind::tf32, hi / lo split per tile by five splitter warps in
+//                        shared memory (splitter-bound, ~175 TFLOP/s); also C -= X'X for the blocked Cholesky.
+//   gram_tc_kernel       p < 256 or an odd SM count: single-CTA 128 x 192 tiles, kind::tf32.
+//
+// Anatomy of the single-CTA kernel (one persistent CTA per SM, 512 threads, tile = 128 x 192 of G, k-slice = 32);
+// the pair kernels are described at their definitions:
 //   warp 0      TMA producer: X tile pairs (A: 128 columns, B: 192 columns, 32 rows of X each,
 //               K-major, SWIZZLE_128B) into a 3-deep shared-memory ring, mbarrier complete_tx.
-//   warps 4-7   splitter: hi/lo split of each landed stage.  The split is element-wise, so it is
+//   warps 3-7   splitter: hi/lo split of each landed stage.  The split is element-wise, so it is
 //               independent of the swizzle: lo goes to a 2-deep ring with the same layout; the raw
 //               buffer is used as `hi` directly (the tensor core ignores the 13 low bits) or is
 //               overwritten with hi (exact_hi = 1).  fence.proxy.async + mbarrier arrive.

@@ -12,12 +12,16 @@ matrix, the coarse-Lanczos rho, the factorisation / inverse and all ADMM iterati
             X already resident in HBM (float32, column-major) when the timed region starts;
   e2e       the same with X, y in pinned HOST memory: the host->device copy of the 40 GB design
             and the device->host read of the solutions are inside every timed step;
-  roofline  the persistent iteration kernel (fadmm_tall.cu): algorithmic bytes per iteration
-            4 p (p + 1) + 64 p divided by the device time per iteration, against measured HBM peak;
+  roofline  the dominant kernel of the step, the tensor-core Gram kernel (gram_tc.cu): algorithmic flops
+            n p (p + 1) / its device time against the measured sustained dense bf16 rate (`executed` = the 3.2x
+            it really executes: three fp16 products per element); roofline_iteration: the persistent iteration
+            kernel (fadmm_tall.cu), algorithmic bytes per iteration 4 p (p + 1) + 64 p / device time per
+            iteration against measured HBM peak; `traffic` of both from profiles/traffic.json (ncu captures);
   cpu_baseline  the CPU oracle (restated reference, OpenBLAS on all host cores) on a bounded sample.
 
 N > 1 (torchrun, one rank per GPU): the same n x p problem row-sharded over the ranks (strong
-scaling): global standardisation / X'y / Gram by NCCL all-reduce, iterations replicated.
+scaling): global standardisation / X'y / Gram by NCCL all-reduce, factorisation replicated, iterations
+sharded over the rows of K^-1 with the exchange fused into the kernel over NVLink peer memory.
 """
 import argparse
 import ctypes as C
@@ -383,7 +387,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "lasso_tall_n%d_p%d_%dlambda" % (n, p, nl), "n": n, "p": p, "nlambda": nl,
                    "standardize": True, "intercept": True, "eps_abs": 1e-5, "eps_rel": 1e-5, "maxit": 10000, "rho": "auto",
-                   "sharding": "rows over %d rank(s), Gram all-reduce, iterations replicated" % world,
+                   "sharding": "rows over %d rank(s), Gram all-reduce, iterations sharded over peer memory" % world,
                    "l2": "inputs (%.1f GB) exceed L2; no flush needed" % (4.0 * n_local * p / 1e9)},
         "path_wall_s": dev_s / args.steps, "host_wall_s_per_step": wall_s / args.steps,
         "niter_path": niter_path, "iters_per_sec_steady": niter_path / T["iterate"],
