@@ -129,3 +129,43 @@ def test_host_lanczos_matches_oracle_on_cpu():
     ev_p = float(out[0])
     assert abs(ev_p - ev_o) < 2e-5 * ev_o          # same algorithm; the mat-vec sums in another order
     assert int(out[1]) == info["nmatvec"] and int(out[3]) == info["converged"]
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path, K):
+    """The drop-in boundary is a C ABI: the header must compile as C99 and as C++, and a plain C program must
+    link against the shared library and resolve every entry point (it only asks for the version and, without a
+    GPU, gets B200ADMM_ENODEVICE from a solver call -- no compute on CPU)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    hdr = os.path.join(ROOT, "include", "b200admm.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run([shutil.which("g++") or gcc, "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "b200admm.h"
+int main(void) {
+    double x[6] = {1, 2, 3, 4, 5, 7}, y[3] = {1, 2, 3}, lam[1] = {0.1};
+    b200admm_data d; b200admm_opts o; b200admm_path P;
+    memset(&d, 0, sizeof d); memset(&P, 0, sizeof P);
+    d.n = 3; d.p = 2; d.dtype = B200ADMM_F64_HOST; d.x = x; d.y = y;
+    o.maxit = 10; o.eps_abs = 1e-5; o.eps_rel = 1e-5; o.rho = -1.0;
+    int rc = b200admm_lasso(&d, lam, 1, 1, 1e-4, 1, 1, &o, &P);
+    printf("%d %d %s\n", b200admm_version(), rc, rc ? b200admm_last_error() : "ok");
+    if (rc == 0) b200admm_free_path(&P);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(K.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libb200admm.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split(None, 2)
+    assert out[0] == "100"
+    import torch
+    if not torch.cuda.is_available():
+        assert int(out[1]) == -2, out                     # B200ADMM_ENODEVICE: no CPU fallback behind the ABI
