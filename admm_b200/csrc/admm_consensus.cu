@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(CT) cons_rhs_kernel(const float* __restrict__ 
     }
 }
 // Woodbury tail: x = (rhs - t) / frho
-__global__ void __launch_bounds__(CT) cons_woodbury_kernel(const float* __restrict__ rhs, const float* __restrict__ t, float frho, int p, float* __restrict__ x)
+__global__ void __launch_bounds__(CT) cons_woodbury_kernel(const float* __restrict__ rhs, const float* t, float frho, int p, float* x)   /* t may alias x (in place) */
 {
     for (int j = blockIdx.x * CT + threadIdx.x; j < p; j += gridDim.x * CT) x[j] = (rhs[j] - t[j]) / frho;
 }

@@ -62,16 +62,6 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsig
 {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
 // all CTAs of the (co-resident, cooperative) grid
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target)
 {
