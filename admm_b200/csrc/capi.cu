@@ -14,6 +14,7 @@
 #include "comm.h"
 
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
@@ -146,11 +147,21 @@ double wall_now()
 // ---------------------------------------------------------------------------------------------
 void make_lambda_grid(double lmax, double ratio, int nl, std::vector<double>& out)
 {
-    // lambda.setLinSpaced(nlambda, log(lmax), log(lmin)).exp()   (Lasso.cpp:86-88)
+    // lambda.setLinSpaced(nlambda, log(lmax), log(lmin)).exp()   (Lasso.cpp:86-88), Eigen 3.3 semantics:
+    // one value -> `high` (so nlambda = 1 fits at lmin_ratio * lmax, not at lmax); otherwise the end nearer
+    // zero is reached by stepping from the other end (low + i step, last = high; or first = low,
+    // high - (n - 1 - i) step when |high| < |low|).
     out.resize(nl);
     const double lo = std::log(lmax), hi = std::log(ratio * lmax);
-    const double step = nl > 1 ? (hi - lo) / (nl - 1) : 0.0;
-    for (int i = 0; i < nl; i++) out[i] = std::exp((i == nl - 1 && nl > 1) ? hi : lo + i * step);
+    if (nl == 1) { out[0] = std::exp(hi); return; }
+    const double step = (hi - lo) / (nl - 1);
+    const bool flip = std::fabs(hi) < std::fabs(lo);
+    for (int i = 0; i < nl; i++) {
+        double v;
+        if (flip) v = (i == 0) ? lo : hi - (double)(nl - 1 - i) * step;
+        else v = (i == nl - 1) ? hi : lo + (double)i * step;
+        out[i] = std::exp(v);
+    }
 }
 
 void free_path(b200admm_path* out)
@@ -615,6 +626,16 @@ int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int
         for (size_t i = 0; i < b.size(); i++) begin[i] = b[i];
         return (int)b.size() - 1;
     } catch (...) { return -1; }
+}
+
+int b200admm_k_lambda_grid(double lmax, double lmin_ratio, int nlambda, double* out)
+{
+    return fenced([&] {
+        if (!(lmax > 0) || !(lmin_ratio > 0) || nlambda < 1 || !out) throw ArgError("lambda grid: bad arguments");
+        std::vector<double> g;
+        make_lambda_grid(lmax, lmin_ratio, nlambda, g);
+        for (int i = 0; i < nlambda; i++) out[i] = g[i];
+    });
 }
 
 int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v, void* out)

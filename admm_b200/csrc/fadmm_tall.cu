@@ -206,9 +206,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
         const bool tracing = (a.trace != nullptr) && (k == a.trace_lambda);
 
         // rhs = XY - adj_y + rho * adj_z from the stored extrapolation (cold start: zeros).  On a warm start this
-        // is the rhs the last iteration already left in shared memory (the loop exits before a new extrapolation
-        // is formed); a sharded run keeps it there, because it stores adj_* for its own rows only.
-        if (k == 0 || NR == 1)
+        // is the rhs already in shared memory: a converged lambda leaves the loop before a new extrapolation is
+        // formed, a lambda that ran out of iterations leaves right after phase [C] wrote the rhs of the new one.
+        // It must NOT be rebuilt from global adj_*: after an exhausted lambda the other CTAs' rows of adj_* have
+        // just been written with no grid barrier in between (and a sharded run stores its own rows only).
+        if (k == 0)
         for (int v = tid; v < nvec; v += TP_THREADS) {
             const float4 xy = __ldg(reinterpret_cast<const float4*>(a.XY) + v);
             const float4 ay = ldcg4(adj_y + 4 * v), az = ldcg4(adj_z + 4 * v);

@@ -1365,8 +1365,15 @@ bool gram_tn_tensor(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float
             CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr = true;
         }
-        const char* dbg_env = getenv("B200ADMM_GRAM_DBG");     // timing experiments only (results are wrong when set)
-        gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, I0, nJ, ntiles, exact_hi ? 1 : 0, dbg_env ? atoi(dbg_env) : 0);
+        // timing experiments (skip the split / the tensor work: WRONG results) exist only in builds made with
+        // -DB200ADMM_GRAM_DEBUG; a release build passes 0 and the compiler drops the branches
+#ifdef B200ADMM_GRAM_DEBUG
+        const char* dbg_env = getenv("B200ADMM_GRAM_DBG");
+        const int dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+        const int dbg = 0;
+#endif
+        gram_tc_kernel<<<grid, GT_THREADS, SMEM_BYTES, s>>>(mapA, mapB, G, (int)p, (long long)ld, nk, I0, nJ, ntiles, exact_hi ? 1 : 0, dbg);
         KERNEL_CHECK();
     }
     }

@@ -227,14 +227,33 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         if (use_f16) xty_work.alloc(gram_f16_xty_work_floats(n_local, pw));
         DevBuf<double> slab[2];
         if (esz == 8) { slab[0].alloc((size_t)n_local * (size_t)pw); slab[1].alloc((size_t)n_local * (size_t)pw); }
-        std::vector<cudaEvent_t> landed(npan), freed(2);
-        for (auto& e : landed) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto& e : freed) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        cudaStream_t cs = copy_stream();
-        cudaEvent_t start_ev;
-        CUDA_CHECK(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventRecord(start_ev, s));
-        CUDA_CHECK(cudaStreamWaitEvent(cs, start_ev, 0));
+        // Events and the copy stream are owned by a guard declared AFTER every device buffer the copies land in
+        // (Xs, slab[]): on any exit path -- a declined shape, the fp16 overflow flag, a CUDA or NCCL error --
+        // its destructor runs first, waits for the copy stream and destroys the events, so no block returns to
+        // the cache while a DMA may still be writing into it.
+        struct IngestGuard {
+            std::vector<cudaEvent_t> landed, freed;
+            cudaEvent_t start_ev = nullptr;
+            cudaStream_t cs = nullptr;
+            ~IngestGuard()
+            {
+                if (cs) cudaStreamSynchronize(cs);
+                for (auto& e : landed) if (e) cudaEventDestroy(e);
+                for (auto& e : freed) if (e) cudaEventDestroy(e);
+                if (start_ev) cudaEventDestroy(start_ev);
+            }
+        } ig;
+        ig.landed.assign(npan, nullptr);
+        ig.freed.assign(2, nullptr);
+        ig.cs = copy_stream();
+        for (auto& e : ig.landed) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ig.freed) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ig.start_ev, cudaEventDisableTiming));
+        std::vector<cudaEvent_t>& landed = ig.landed;
+        std::vector<cudaEvent_t>& freed = ig.freed;
+        cudaStream_t cs = ig.cs;
+        CUDA_CHECK(cudaEventRecord(ig.start_ev, s));
+        CUDA_CHECK(cudaStreamWaitEvent(cs, ig.start_ev, 0));
         for (int k = 0; k < npan; k++) {
             const i64 c0 = pan_begin[k], pc = pan_begin[k + 1] - c0;
             float* dstp = Xs.p + c0 * ldx;
@@ -275,9 +294,6 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
         fetch_std_stats(s, p, flag, d_meanX.p, d_scaleX.p, st);
         T.gram = tm.stop();                                   // copy + DataStd + X'y + Gram, overlapped
         CUDA_CHECK(cudaStreamSynchronize(cs));
-        for (auto& e : landed) cudaEventDestroy(e);
-        for (auto& e : freed) cudaEventDestroy(e);
-        cudaEventDestroy(start_ev);
         T.ingest = 0; T.standardize = 0;
     } else {
     // ---- ingest ------------------------------------------------------------------------------

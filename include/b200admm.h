@@ -131,7 +131,9 @@ int b200admm_bp(const b200admm_data* d, const b200admm_opts* opts, b200admm_path
  * b200admm_comm_id writes a B200ADMM_COMM_ID_BYTES identifier on one rank; the host program
  * broadcasts it and every rank calls b200admm_comm_init.  After that b200admm_lasso/_enet
  * treat `d` as this rank's row block of a taller matrix (global standardisation and Gram via
- * all-reduce, iterations replicated -- bit-identical to the single-GPU solver), and
+ * all-reduce; the factorisation is replicated and the iterations are sharded over the rows of K^-1
+ * with the exchange fused into the persistent kernel over NVLink peer memory -- every rank returns
+ * the identical result, equal to the single-GPU solver's up to summation order), and
  * b200admm_parlasso runs the reference's consensus algorithm with one block per rank
  * (src/PADMMLasso.h:163-178) and one all-reduce per iteration. */
 #define B200ADMM_COMM_ID_BYTES 128
@@ -186,6 +188,10 @@ int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g /* p x p, f
  * (returns the number of panels, begin[0 .. npanels] their first columns; -1 on bad arguments). */
 int b200admm_k_gram_plan(int ntiles, int npairs, int nk, int* cover, long long* per_pair, int* nslices, int* split_tiles);
 int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int cap);
+/* Host-only: the default lambda sequence of admm_lasso / admm_enet (src/Lasso.cpp:78-89,
+ * `lambda.setLinSpaced(nlambda, log(lmax), log(lmin)).exp()` with Eigen's LinSpaced semantics: a single
+ * value is the HIGH end, i.e. nlambda = 1 fits at lmin_ratio * lmax).  out: nlambda doubles. */
+int b200admm_k_lambda_grid(double lmax, double lmin_ratio, int nlambda, double* out);
 int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v, void* out);
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host);                 /* lower, in place */
 int b200admm_k_spd_inverse_f32(void* a, int64_t p, void* work, int* info_host); /* a <- a^-1 (full) */

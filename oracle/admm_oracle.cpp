@@ -706,9 +706,18 @@ struct BpModel {
 // lambda grid  (/root/reference/src/Lasso.cpp:78-89)
 void make_lambda_grid(double lmax, double ratio, int nl, double* out)
 {
-    const double lo = std::log(lmax), hi = std::log(ratio * lmax);
-    const double step = nl > 1 ? (hi - lo) / (nl - 1) : 0.0;
-    for (int i = 0; i < nl; i++) out[i] = std::exp(i == nl - 1 && nl > 1 ? hi : lo + i * step);
+    // Eigen's LinSpaced (3.3): a single point is `high`; else low + i*step with the last point forced to
+    // high, or -- when |high| < |low| -- high - (nl-1-i)*step with the first point forced to low.
+    const double a = std::log(lmax), b = std::log(ratio * lmax);
+    if (nl == 1) { out[0] = std::exp(b); return; }
+    const double h = (b - a) / (nl - 1);
+    if (std::fabs(b) < std::fabs(a)) {
+        out[0] = std::exp(a);
+        for (int i = 1; i < nl; i++) out[i] = std::exp(b - (double)(nl - 1 - i) * h);
+    } else {
+        for (int i = 0; i < nl - 1; i++) out[i] = std::exp(a + (double)i * h);
+        out[nl - 1] = std::exp(b);
+    }
 }
 
 double now_s()

@@ -82,3 +82,43 @@ def test_panel_schedule_rejects_bad_arguments(L):
     buf = np.zeros(4, dtype=np.int64)
     assert L.b200admm_k_panel_schedule(0, 256, buf.ctypes.data, 4) == -1
     assert L.b200admm_k_panel_schedule(100000, 256, buf.ctypes.data, 4) == -1      # not enough room
+
+
+def eigen_linspaced(n, low, high):
+    """Eigen 3.3 DenseBase::setLinSpaced(n, low, high) for floating point (NullaryFunctors.h, linspaced_op):
+    n == 1 -> high; |high| < |low| -> first = low, rest = high - (n-1-i) step; else low + i step, last = high."""
+    if n == 1:
+        return np.array([high])
+    step = (high - low) / (n - 1)
+    i = np.arange(n, dtype=np.float64)
+    if abs(high) < abs(low):
+        v = high - (n - 1 - i) * step
+        v[0] = low
+    else:
+        v = low + i * step
+        v[-1] = high
+    return v
+
+
+@pytest.mark.parametrize("lmax,ratio,nl", [(0.37, 1e-4, 100), (512.0, 1e-2, 100), (3.0, 1e-4, 2), (0.9, 0.01, 1), (40.0, 1e-4, 1), (1.7, 0.5, 7)])
+def test_lambda_grid_has_eigen_linspaced_semantics(L, lmax, ratio, nl):
+    """src/Lasso.cpp:86-88.  nlambda = 1 must give lmin_ratio * lmax (setLinSpaced(1, low, high) is `high`),
+    in the library and in the oracle alike."""
+    out = np.zeros(nl)
+    assert L.b200admm_k_lambda_grid(lmax, ratio, nl, out.ctypes.data) == 0
+    import math
+    want = np.array([math.exp(v) for v in eigen_linspaced(nl, math.log(lmax), math.log(ratio * lmax))])   # libm, as std::exp
+    assert np.array_equal(out, want), np.abs(out / want - 1).max()
+    if nl == 1:
+        assert out[0] == math.exp(math.log(ratio * lmax)) and out[0] < lmax
+
+
+def test_oracle_single_lambda_default_is_the_low_end():
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(4)
+    x = np.asfortranarray(rng.normal(size=(60, 8)))
+    y = x[:, 0] - 0.5 * x[:, 1] + 0.1 * rng.normal(size=60)
+    one = O.lasso_path(x, y, nlambda=1)
+    two = O.lasso_path(x, y, nlambda=2)
+    assert np.isclose(one["lambda_"][0], two["lambda_"][1], rtol=1e-14)
+    assert np.isclose(one["lambda_"][0], 1e-4 * two["lambda_"][0], rtol=1e-12)
