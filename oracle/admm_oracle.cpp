@@ -27,6 +27,7 @@
 // (index) order and adding an exact zero is exact; support := {i : z_i != 0}.
 #include "linalg.hpp"
 #include "lanczos.hpp"
+#include "synth_stream.hpp"
 #include <cstdio>
 #include <chrono>
 
@@ -796,6 +797,149 @@ int oracle_tall_path_from_gram(float* G, const float* XY, i64 p, int enet, doubl
         std::copy(m.s.z.begin(), m.s.z.end(), z_out + (size_t)k * p);
     }
     if (aux_out) { aux_out[0] = m.s.rho; aux_out[1] = m.ev_estimate; aux_out[2] = m.lz.nmatvec; aux_out[3] = t1 - t0; }
+    return 0;
+}
+
+// The synthetic benchmark design (see synth_stream.hpp): rows [row0, row0 + nrows) of the global matrix
+// into X (column-major, leading dimension nrows) and y.  Bit-identical to the library's CUDA generator.
+int oracle_synth_f32(float* X, float* y, i64 nrows, i64 p, i64 row0, unsigned long long seed,
+                     float mean_x, float sd_x, int nsig, float noise)
+{
+    synth::fill_x(X, nrows, nrows, p, row0, seed, mean_x, sd_x);
+    if (y) synth::fill_y(X, nrows, nrows, p, row0, seed, nsig, noise, y);
+    return 0;
+}
+
+// Full-size tall lasso on the synthetic design WITHOUT holding X (n x p floats = 40 GB at the headline
+// size): the design is regenerated chunk by chunk for each of the three passes DataStd + Gram need
+//   pass 1  column sums -> meanX; y as a whole -> meanY, scaleY            (DataStd.h:128-133, :98-104)
+//   pass 2  centred sums of squares -> scaleX = |x - mean| / sqrt(n)       (DataStd.h:134-150)
+//   pass 3  standardise the chunk, XY += Xc'y, G += Xc'Xc (SYRK)           (ADMMLassoTall.h:172,191-192)
+// then the reference's lambda grid and warm-started path (Lasso.cpp:78-124) on (G, XY).
+// Per-column statistics are float sums per chunk combined in double (the reference sums a whole column in
+// float; the difference is summation order only).  Generation time is reported separately: X is the
+// caller's input, not part of the reference's work.
+//   times_out (8): generate, standardize (statistics + apply), gram (+ X'y), lanczos + cholesky, iterations, total, 0, 0
+//   aux_out (6): rho, eig estimate, lambda0, scaleY, meanY, total iterations
+int oracle_tall_fit_synth(i64 n, i64 p, unsigned long long seed, float mean_x, float sd_x, int nsig, float noise,
+                          i64 chunk_rows, int nlambda, double lmin_ratio, int maxit, double eps_abs, double eps_rel, double rho,
+                          double* lambda_out, double* beta_out /* (p+1) x nl */, int* niter_out,
+                          double* times_out, double* aux_out, float* gram_out /* p x p lower, optional */, float* xy_out /* optional */)
+{
+    if (!(n > p) || p < 3 || chunk_rows < 4) return -1;
+    chunk_rows = (chunk_rows / 4) * 4;
+    const double t_begin = now_s();
+    double t_gen = 0, t_std = 0, t_gram = 0;
+    std::vector<float> Xc((size_t)chunk_rows * p), yv(n);
+    std::vector<double> colsum(p, 0.0), colsq(p, 0.0);
+    std::vector<float> meanX(p), scaleX(p), invX(p);
+
+    // ---- pass 1: y (needs the first nsig columns of every chunk) and column sums ----------------------------
+    for (i64 r0 = 0; r0 < n; r0 += chunk_rows) {
+        const i64 nr = std::min(chunk_rows, n - r0);
+        double ta = now_s();
+        synth::fill_x(Xc.data(), nr, nr, p, r0, seed, mean_x, sd_x);
+        synth::fill_y(Xc.data(), nr, nr, p, r0, seed, nsig, noise, yv.data() + r0);
+        double tb = now_s();
+#pragma omp parallel for schedule(static)
+        for (i64 j = 0; j < p; j++) colsum[j] += (double)(mean(Xc.data() + j * nr, nr) * (float)nr);
+        t_gen += tb - ta; t_std += now_s() - tb;
+    }
+    double ta = now_s();
+    for (i64 j = 0; j < p; j++) meanX[j] = (float)(colsum[j] / (double)n);
+    const float n_invsqrt = float(1.0 / std::sqrt(float(n)));
+    const float meanY = mean(yv.data(), n);
+    for (i64 i = 0; i < n; i++) yv[i] -= meanY;
+    const float scaleY = norm2(yv.data(), n) * n_invsqrt;
+    for (i64 i = 0; i < n; i++) yv[i] /= scaleY;
+    t_std += now_s() - ta;
+
+    // ---- pass 2: centred sums of squares ----------------------------------------------------------------------
+    for (i64 r0 = 0; r0 < n; r0 += chunk_rows) {
+        const i64 nr = std::min(chunk_rows, n - r0);
+        ta = now_s();
+        synth::fill_x(Xc.data(), nr, nr, p, r0, seed, mean_x, sd_x);
+        double tb = now_s();
+#pragma omp parallel for schedule(static)
+        for (i64 j = 0; j < p; j++) {
+            const float* c = Xc.data() + j * nr;
+            const float mu = meanX[j];
+            float s0 = 0, s1 = 0, s2 = 0, s3 = 0; i64 i = 0;
+            for (; i + 4 <= nr; i += 4) {
+                const float a = c[i] - mu, b = c[i + 1] - mu, cc = c[i + 2] - mu, d = c[i + 3] - mu;
+                s0 += a * a; s1 += b * b; s2 += cc * cc; s3 += d * d;
+            }
+            for (; i < nr; i++) { const float a = c[i] - mu; s0 += a * a; }
+            colsq[j] += (double)((s0 + s1) + (s2 + s3));
+        }
+        t_gen += tb - ta; t_std += now_s() - tb;
+    }
+    for (i64 j = 0; j < p; j++) {
+        scaleX[j] = (float)std::sqrt(colsq[j]) * n_invsqrt;
+        invX[j] = float(1.0 / scaleX[j]);
+    }
+
+    // ---- pass 3: standardise, X'y, Gram ---------------------------------------------------------------------
+    std::vector<float> G((size_t)p * p, 0.f), XY(p, 0.f), xyc(p);
+    for (i64 r0 = 0; r0 < n; r0 += chunk_rows) {
+        const i64 nr = std::min(chunk_rows, n - r0);
+        ta = now_s();
+        synth::fill_x(Xc.data(), nr, nr, p, r0, seed, mean_x, sd_x);
+        double tb = now_s();
+#pragma omp parallel for schedule(static)
+        for (i64 j = 0; j < p; j++) {
+            float* c = Xc.data() + j * nr;
+            const float mu = meanX[j], inv = invX[j];
+            for (i64 i = 0; i < nr; i++) c[i] = (c[i] - mu) * inv;
+        }
+        double tc = now_s();
+        gemv_t(Xc.data(), nr, p, yv.data() + r0, xyc.data());
+        for (i64 j = 0; j < p; j++) XY[j] += xyc[j];
+        if (blas().on && fits_int(nr) && fits_int(p)) {
+            int N = (int)p, K = (int)nr; float al = 1.f, be = 1.f;
+            blas().ssyrk("L", "T", &N, &K, &al, Xc.data(), &K, &be, G.data(), &N);
+        } else {
+            std::vector<float> Gc((size_t)p * p, 0.f);
+            gram_tn_lower_plain(Xc.data(), nr, p, Gc.data());
+            for (size_t q = 0; q < G.size(); q++) G[q] += Gc[q];
+        }
+        double td = now_s();
+        t_gen += tb - ta; t_std += tc - tb; t_gram += td - tc;
+    }
+    { std::vector<float>().swap(Xc); }
+    if (gram_out) std::copy(G.begin(), G.end(), gram_out);
+    if (xy_out) std::copy(XY.begin(), XY.end(), xy_out);
+
+    // ---- lambda grid + path (Lasso.cpp:78-124) ------------------------------------------------------------
+    TallLasso m(p, XY.data(), eps_abs, eps_rel);
+    std::vector<double> lam(nlambda);
+    make_lambda_grid((double)m.lambda0 / (double)n * (double)scaleY, lmin_ratio, nlambda, lam.data());
+    double t_setup = 0, t_iter = 0;
+    long long total_it = 0;
+    std::vector<float> coef(p);
+    for (int k = 0; k < nlambda; k++) {
+        const double il = lam[k] * (double)n / (double)scaleY;
+        ta = now_s();
+        if (k == 0) { const int info = m.init(G, il, rho); if (info != 0) return info < 0 ? info : 100 + info; }
+        else m.init_warm(il);
+        double tb = now_s();
+        niter_out[k] = m.solve(maxit, nullptr);
+        total_it += niter_out[k];
+        t_setup += tb - ta; t_iter += now_s() - tb;
+        coef = m.s.z;
+        // DataStd::recover, flag 3 (DataStd.h:183-207): stored entries only
+        float sacc = 0.f;
+        for (i64 j = 0; j < p; j++) if (coef[j] != 0.f) { coef[j] /= scaleX[j]; coef[j] *= scaleY; sacc += coef[j] * meanX[j]; }
+        double* col = beta_out + (size_t)k * (p + 1);
+        col[0] = (double)(meanY - sacc);
+        for (i64 j = 0; j < p; j++) col[j + 1] = coef[j];
+        lambda_out[k] = lam[k];
+    }
+    if (times_out) {
+        times_out[0] = t_gen; times_out[1] = t_std; times_out[2] = t_gram; times_out[3] = t_setup; times_out[4] = t_iter;
+        times_out[5] = now_s() - t_begin; times_out[6] = 0; times_out[7] = 0;
+    }
+    if (aux_out) { aux_out[0] = m.s.rho; aux_out[1] = m.ev_estimate; aux_out[2] = m.lambda0; aux_out[3] = scaleY; aux_out[4] = meanY; aux_out[5] = (double)total_it; }
     return 0;
 }
 

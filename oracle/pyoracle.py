@@ -21,7 +21,7 @@ c_ip = C.POINTER(C.c_int)
 
 
 def build(force=False):
-    src = [os.path.join(HERE, f) for f in ("admm_oracle.cpp", "linalg.hpp", "lanczos.hpp")]
+    src = [os.path.join(HERE, f) for f in ("admm_oracle.cpp", "linalg.hpp", "lanczos.hpp", "synth_stream.hpp")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return LIB_PATH
@@ -187,3 +187,35 @@ def tall_path_from_gram(G, XY, lambda_internal, enet=False, alpha=1.0, maxit=100
     if rc != 0:
         raise RuntimeError(f"oracle_tall_path_from_gram failed rc={rc}")
     return dict(z=z, niter=niter, rho=aux[0], eig=aux[1], nmatvec=int(aux[2]), setup_s=aux[3], trace=trace)
+
+
+def synth_f32(nrows, p, row0=0, seed=123, mean_x=0.0, sd_x=2.0, nsig=100, noise=1.0):
+    """Rows [row0, row0 + nrows) of the synthetic benchmark design, bit-identical to the library's CUDA
+    generator (b200admm_synth_f32).  Returns (X float32 Fortran-ordered nrows x p, y float32)."""
+    X = np.empty((nrows, p), dtype=np.float32, order="F")
+    y = np.empty(nrows, dtype=np.float32)
+    lib().oracle_synth_f32(_fp(X), _fp(y), c_i64(nrows), c_i64(p), c_i64(row0), C.c_ulonglong(seed),
+                           C.c_float(mean_x), C.c_float(sd_x), C.c_int(nsig), C.c_float(noise))
+    return X, y
+
+
+def tall_fit_synth(n, p, seed=123, mean_x=0.0, sd_x=2.0, nsig=100, noise=1.0, chunk_rows=32768, nlambda=100,
+                   lambda_min_ratio=1e-4, maxit=10000, eps_abs=1e-5, eps_rel=1e-5, rho=-1.0, want_gram=False):
+    """admm_lasso(x, y)$penalty(nlambda)$fit() of the reference on the full synthetic design, X streamed in row
+    chunks (never resident).  Returns lambda, beta[(p+1) x nl], niter, times (s) and rho/eig/lambda0/scaleY/meanY."""
+    lam = np.zeros(nlambda)
+    beta = np.zeros((p + 1, nlambda), order="F")
+    niter = np.zeros(nlambda, dtype=np.int32)
+    times = np.zeros(8)
+    aux = np.zeros(6)
+    G = np.zeros((p, p), dtype=np.float32, order="F") if want_gram else None
+    xy = np.zeros(p, dtype=np.float32) if want_gram else None
+    rc = lib().oracle_tall_fit_synth(
+        c_i64(n), c_i64(p), C.c_ulonglong(seed), C.c_float(mean_x), C.c_float(sd_x), C.c_int(nsig), C.c_float(noise),
+        c_i64(chunk_rows), C.c_int(nlambda), C.c_double(lambda_min_ratio), C.c_int(maxit), C.c_double(eps_abs),
+        C.c_double(eps_rel), C.c_double(rho), _dp(lam), _dp(beta), _ip(niter), _dp(times), _dp(aux), _fp(G), _fp(xy))
+    if rc != 0:
+        raise RuntimeError(f"oracle_tall_fit_synth failed rc={rc}")
+    t = dict(zip(("generate", "standardize", "gram", "lanczos_cholesky", "iterations", "total"), times[:6].tolist()))
+    return dict(lambda_=lam, beta=beta, niter=niter, times=t, rho=aux[0], eig=aux[1], lambda0=aux[2], scaleY=aux[3],
+                meanY=aux[4], gram=G, xy=xy)
