@@ -19,11 +19,11 @@ COMM_ID_BYTES = 128
 EXPORTS = [
     "b200admm_lasso", "b200admm_enet", "b200admm_parlasso", "b200admm_free_path",
     "b200admm_lad", "b200admm_free_dense", "b200admm_bp",
-    "b200admm_comm_id", "b200admm_comm_init", "b200admm_comm_destroy",
-    "b200admm_last_error", "b200admm_version", "b200admm_launch_count", "b200admm_last_gram_seconds", "b200admm_stream", "b200admm_release_cache", "b200admm_device_info", "b200admm_set_trace",
+    "b200admm_comm_id", "b200admm_comm_init", "b200admm_comm_destroy", "b200admm_comm_suspend", "b200admm_set_capture",
+    "b200admm_last_error", "b200admm_version", "b200admm_launch_count", "b200admm_last_gram_seconds", "b200admm_last_work", "b200admm_stream", "b200admm_release_cache", "b200admm_device_info", "b200admm_set_trace",
     "b200admm_synth_f32",
     "b200admm_k_standardize_f32", "b200admm_k_gram_f32", "b200admm_k_gemv_t_f32",
-    "b200admm_k_gram_plan", "b200admm_k_panel_schedule", "b200admm_k_lambda_grid",
+    "b200admm_k_gram_plan", "b200admm_k_panel_schedule", "b200admm_k_lambda_grid", "b200admm_k_coarse_eig_f32",
     "b200admm_k_chol_f32", "b200admm_k_spd_inverse_f32", "b200admm_k_fused_zu_f32",
 ]
 
@@ -75,6 +75,8 @@ def lib():
         L.b200admm_last_error.restype = C.c_char_p
         L.b200admm_launch_count.restype = C.c_ulonglong
         L.b200admm_last_gram_seconds.restype = C.c_double
+        L.b200admm_last_work.argtypes = [C.c_void_p]
+        L.b200admm_last_work.restype = None
         L.b200admm_stream.restype = C.c_void_p
         L.b200admm_release_cache.restype = None
         L.b200admm_lasso.argtypes = [C.POINTER(Data), C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
@@ -92,6 +94,10 @@ def lib():
         L.b200admm_comm_id.argtypes = [C.c_void_p]
         L.b200admm_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b200admm_comm_destroy.restype = None
+        L.b200admm_comm_suspend.argtypes = [C.c_int]
+        L.b200admm_comm_suspend.restype = None
+        L.b200admm_set_capture.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200admm_set_capture.restype = None
         L.b200admm_device_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
         L.b200admm_set_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.b200admm_set_trace.restype = None
@@ -104,6 +110,7 @@ def lib():
         L.b200admm_k_panel_schedule.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         L.b200admm_k_lambda_grid.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.b200admm_k_gemv_t_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.b200admm_k_coarse_eig_f32.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p]
         L.b200admm_k_chol_f32.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]
         L.b200admm_k_spd_inverse_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
         L.b200admm_k_fused_zu_f32.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_double, C.c_double, C.c_int, C.c_double,
@@ -209,3 +216,37 @@ class trace:
     @property
     def rows(self):
         return self.buf[: self.n.value]
+
+
+class capture:
+    """Context manager: receive the standardised Gram matrix X'X (before rho is added) and X'y of the tall lasso /
+    enet fits made inside the block (parity checks at sizes where X cannot go to a CPU program)."""
+
+    def __init__(self, p):
+        self.gram = np.zeros((p, p), dtype=np.float32, order="F")
+        self.xy = np.zeros(p, dtype=np.float32)
+        self.stats = np.zeros(2 * p + 2, dtype=np.float32)
+        self.p = p
+
+    def __enter__(self):
+        lib().b200admm_set_capture(self.gram.ctypes.data, self.xy.ctypes.data, self.stats.ctypes.data)
+        return self
+
+    def __exit__(self, *a):
+        lib().b200admm_set_capture(None, None, None)
+
+    @property
+    def meanX(self):
+        return self.stats[:self.p]
+
+    @property
+    def scaleX(self):
+        return self.stats[self.p:2 * self.p]
+
+    @property
+    def meanY(self):
+        return float(self.stats[2 * self.p])
+
+    @property
+    def scaleY(self):
+        return float(self.stats[2 * self.p + 1])

@@ -462,6 +462,10 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     const double eps_abs = rq.opts.eps_abs, eps_rel = rq.opts.eps_rel;
     const float gamma = sprad;
     const float sqrt_sprad = std::sqrt(sprad);
+    // algorithmic bytes of the iteration phase: a regular step reads all of X (4 n p), an
+    // active-set step the nnz_k support columns (4 n nnz_k); the z step reads the nnz_{k+1} columns of the new
+    // support; 12 n-vectors of traffic besides.  Data dependent, so it is accumulated while the loop runs.
+    double work_bytes = 0, work_regular = 0, work_active = 0;
     tm.start();
     for (int k = 0; k < nl; k++) {
         const float lambda = (float)(lam[k] * (double)n / (double)scaleY);      // Lasso.cpp:99, stored as Scalar
@@ -475,6 +479,8 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             const double eps_primal = std::max((double)std::sqrt((float)sAx2), (double)std::sqrt((float)sz2)) * eps_rel + std::sqrt((double)n) * eps_abs;
             const double eps_dual = (double)(sqrt_sprad * std::sqrt((float)sy2)) * eps_rel + std::sqrt((double)p) * eps_abs;
             const float frho = (float)rho;
+            const int nnz_before = nnz;
+            int step_kind = 0;                                             // 0: x = 0 shortcut, 1: regular, 2: active set
             // ---------------- x step ----------------
             if (!rq.enet && (double)lambda > (double)lambda0 - 1e-5) {
                 if (nnz > 0) { x.zero(s); nnz = 0; CUDA_CHECK(cudaMemsetAsync(nnz_dev.p, 0, sizeof(int), s)); }
@@ -504,6 +510,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                     }
                 }
                 iter_counter++;
+                step_kind = regular ? 1 : 2;
                 // the new support size stays on the device: a regular step can grow the support to anything up to p,
                 // an active-set step can only shrink it
                 nnz_bound = regular ? (int)std::min<i64>(p, 2147483647LL) : nnz;
@@ -523,6 +530,9 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             const double resid_primal = (double)std::sqrt((float)h[1]);
             sAx2 = h[2]; sz2 = h[3]; sy2 = h[4];
             nnz = (int)h[5];                                               // exact support size after this iteration's x step
+            work_bytes += 4.0 * (double)n * (step_kind == 1 ? (double)p : step_kind == 2 ? (double)nnz_before : 0.0)
+                        + 4.0 * (double)n * (double)nnz + 48.0 * (double)n;
+            if (step_kind == 1) work_regular += 1; else if (step_kind == 2) work_active += 1;
             if (tracing && i < tr.cap) {
                 double* row = tr.buf + 5 * (size_t)i;
                 row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
@@ -544,6 +554,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
     T.iterate = tm.stop();
+    g_last_work[0] = work_bytes; g_last_work[1] = work_regular; g_last_work[2] = work_active; g_last_work[3] = 0;
 
     tm.start();
     out->nlambda = nl;

@@ -25,6 +25,7 @@ namespace b200 {
 static thread_local std::string g_last_error;
 unsigned long long g_launch_count = 0;
 double g_last_gram_seconds = 0.0;
+double g_last_work[4] = {0, 0, 0, 0};
 
 int sm_count()
 {
@@ -135,6 +136,12 @@ TraceRequest& trace_request()
 {
     static TraceRequest t;
     return t;
+}
+
+CaptureRequest& capture_request()
+{
+    static CaptureRequest c;
+    return c;
 }
 
 double wall_now()
@@ -432,6 +439,7 @@ int b200admm_version(void) { return B200ADMM_VERSION; }
 unsigned long long b200admm_launch_count(void) { return g_launch_count; }
 double b200admm_last_gram_seconds(void) { return b200::g_last_gram_seconds; }
 void b200admm_release_cache(void) { dev_cache_release(); }
+void b200admm_last_work(double* out4) { if (out4) for (int i = 0; i < 4; i++) out4[i] = b200::g_last_work[i]; }
 void* b200admm_stream(void)
 {
     void* h = nullptr;
@@ -456,6 +464,12 @@ void b200admm_set_trace(double* buf, int cap, int which, int* nrows)
     TraceRequest& t = trace_request();
     t.buf = buf; t.cap = cap; t.which = which; t.nrows = nrows;
     if (nrows) *nrows = 0;
+}
+
+void b200admm_set_capture(float* gram_host, float* xy_host, float* stats_host)
+{
+    CaptureRequest& c = capture_request();
+    c.gram = gram_host; c.xy = xy_host; c.stats = stats_host;
 }
 
 int b200admm_lasso(const b200admm_data* d, const double* lambda_given, int nlambda_given, int nlambda,
@@ -568,6 +582,7 @@ void b200admm_comm_destroy(void)
 {
     try { comm_destroy(); } catch (...) {}
 }
+void b200admm_comm_suspend(int on) { comm().suspended = on != 0; }
 
 // ---- kernel-level entry points ----------------------------------------------------------------
 int b200admm_k_standardize_f32(const void* x_in, void* x_out, void* y_inout, int64_t n, int64_t p,
@@ -644,6 +659,27 @@ int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v,
         Context& c = ctx();
         gemv_t<float>(c.stream, (const float*)a, m, ncol, m, (const float*)v, (float*)out);
         CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int b200admm_k_coarse_eig_f32(const void* sm, int64_t n, float* ev_host, int* info_host)
+{
+    return fenced([&] {
+        Context& c = ctx();
+        if (!sm || !ev_host) throw ArgError("coarse eig: null argument");
+        if (n < 3) throw CodeError(B200ADMM_ELANCZOS, "coarse eigenvalue estimate needs at least 3 variables (Spectra: 1 <= nev < ncv <= n)");
+        DevBuf<float> dv(n), dw(n);
+        eig::LanczosInfo info;
+        cudaStream_t s = c.stream;
+        const float* S = (const float*)sm;
+        auto op = [&](const float* v, float* w) {
+            CUDA_CHECK(cudaMemcpyAsync(dv.p, v, n * sizeof(float), cudaMemcpyHostToDevice, s));
+            gemv_t<float>(s, S, n, n, n, dv.p, dw.p);
+            CUDA_CHECK(cudaMemcpyAsync(w, dw.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+        };
+        *ev_host = eig::coarse_largest_eigenvalue<float>(op, n, &info);
+        if (info_host) { info_host[0] = info.nmatvec; info_host[1] = info.nrestart; info_host[2] = info.converged; }
     });
 }
 

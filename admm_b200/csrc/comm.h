@@ -14,7 +14,8 @@ struct Comm {
     int rank = 0;
     int nranks = 1;
     void* handle = nullptr;       // ncclComm_t
-    bool active() const { return handle != nullptr && nranks > 1; }
+    bool suspended = false;       // b200admm_comm_suspend: calls behave as on a single GPU while set
+    bool active() const { return handle != nullptr && nranks > 1 && !suspended; }
 };
 Comm& comm();
 

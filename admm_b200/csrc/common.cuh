@@ -34,6 +34,7 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 }
 #define CUDA_CHECK(x) ::b200::cuda_check((x), #x, __FILE__, __LINE__)
 extern double g_last_gram_seconds;             // device time of the last tall solver's Gram kernel launches
+extern double g_last_work[4];                  // b200admm_last_work: {algorithmic iteration bytes, regular steps, active-set steps, 0} of the last wide fit
 extern unsigned long long g_launch_count;       // kernels launched by this library (capi.cu)
 #define KERNEL_CHECK() do { ++::b200::g_launch_count; ::b200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); } while (0)
 

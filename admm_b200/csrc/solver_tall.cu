@@ -357,6 +357,16 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     T.gram = tm.stop();
     }
     std::vector<float> h_xy(p);
+    {
+        CaptureRequest& cap = capture_request();
+        if (cap.gram) CUDA_CHECK(cudaMemcpy2DAsync(cap.gram, (size_t)p * 4, G.p, (size_t)ld * 4, (size_t)p * 4, (size_t)p, cudaMemcpyDeviceToHost, s));
+        if (cap.xy) CUDA_CHECK(cudaMemcpyAsync(cap.xy, XY.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (cap.stats) {
+            std::copy(st.meanX.begin(), st.meanX.end(), cap.stats);
+            std::copy(st.scaleX.begin(), st.scaleX.end(), cap.stats + p);
+            cap.stats[2 * p] = st.meanY; cap.stats[2 * p + 1] = st.scaleY;
+        }
+    }
     CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), XY.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     g_last_gram_seconds = gram_kernel_time.total();

@@ -23,6 +23,15 @@ struct TraceRequest {
 };
 TraceRequest& trace_request();
 
+// b200admm_set_capture: host buffers that receive the Gram matrix X'X of the standardised data (before rho is
+// added; p x p, column-major, full symmetric) and X'y of the next tall lasso / enet call (parity checks)
+struct CaptureRequest {
+    float* gram = nullptr;
+    float* xy = nullptr;
+    float* stats = nullptr;       // 2 p + 2 floats: meanX[p], scaleX[p], meanY, scaleY (DataStd)
+};
+CaptureRequest& capture_request();
+
 double wall_now();
 
 struct LassoRequest {

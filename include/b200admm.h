@@ -140,6 +140,10 @@ int b200admm_bp(const b200admm_data* d, const b200admm_opts* opts, b200admm_path
 int  b200admm_comm_id(void* id_out);
 int  b200admm_comm_init(const void* id, int rank, int nranks);
 void b200admm_comm_destroy(void);
+/* on != 0: until switched off again every call treats `d` as a whole matrix on this GPU alone, exactly as if no
+ * communicator were installed (bench.py / the multi-GPU tests fit the undivided problem on one rank to check
+ * the sharded result against it).  Not collective. */
+void b200admm_comm_suspend(int on);
 
 /* ---- utilities ---------------------------------------------------------------------------- */
 const char* b200admm_last_error(void);
@@ -150,6 +154,11 @@ unsigned long long b200admm_launch_count(void);
  * the tensor-core launches only; the `gram` field of b200admm_timing also covers X'y, the operand split
  * and, for host input, the overlapped copy).  bench.py's tensor roofline is computed from it. */
 double b200admm_last_gram_seconds(void);
+/* Work counters of the most recent wide (n <= p) lasso / enet call, whose per-iteration traffic depends on the
+ * support: out4 = {algorithmic bytes of the iteration phase (sum over iterations of 4 n p for a regular step or
+ * 4 n nnz_k for an active-set step, + 4 n nnz_{k+1} for the z step + 48 n of vector traffic), number of regular
+ * steps, number of active-set steps, 0}.  bench.py's HBM roofline of that path is computed from it. */
+void b200admm_last_work(double* out4);
 /* the cudaStream_t every kernel of this library is launched on (for event timing by the host
  * program); NULL if no device is usable */
 void* b200admm_stream(void);
@@ -164,6 +173,12 @@ int  b200admm_device_info(char* name, int name_len, int* sm_count, int64_t* mem_
  * {eps_primal, resid_primal, eps_dual, resid_dual, rho}.  Set before a call; the library
  * fills up to `cap` rows for lambda index `which` and stores the row count in *nrows. */
 void b200admm_set_trace(double* buf, int cap, int which, int* nrows);
+/* Parity checks at sizes where X cannot be handed to a CPU program: the next b200admm_lasso / _enet call with
+ * n > p copies the Gram matrix X'X of the standardised data (float, p x p column-major, full symmetric, BEFORE
+ * rho is added) to gram_host, X'y (p floats) to xy_host and DataStd's statistics to stats_host (2 p + 2 floats:
+ * meanX[p], scaleX[p], meanY, scaleY); any may be NULL, all NULL switches it off.
+ * The copies add device->host traffic to that call: do not time it. */
+void b200admm_set_capture(float* gram_host, float* xy_host, float* stats_host);
 
 /* Synthetic design of the reference's benchmarks (README.md:195-201): X_ij ~ N(mean_x, sd_x^2)
  * i.i.d. (counter-based Philox4x32-10, so any row block can be produced independently),
@@ -193,6 +208,10 @@ int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int
  * value is the HIGH end, i.e. nlambda = 1 fits at lmin_ratio * lmax).  out: nlambda doubles. */
 int b200admm_k_lambda_grid(double lmax, double lmin_ratio, int nlambda, double* out);
 int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v, void* out);
+/* The coarse lambda_max estimate behind the default rho / gamma (src/ADMMLassoTall.h:194-202: Spectra
+ * SymEigsSolver<float, LARGEST_ALGE>(op, 1, 3).compute(10, 0.1)) of the symmetric float32 matrix s (n x n, full
+ * storage, device).  info_host (optional, 3 ints): products with s, restarts, converged flag. */
+int b200admm_k_coarse_eig_f32(const void* s, int64_t n, float* ev_host, int* info_host);
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host);                 /* lower, in place */
 int b200admm_k_spd_inverse_f32(void* a, int64_t p, void* work, int* info_host); /* a <- a^-1 (full) */
 /* fused z + u + residual + norms pass of the accelerated loop on vectors of length len

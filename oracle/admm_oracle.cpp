@@ -822,7 +822,8 @@ int oracle_synth_f32(float* X, float* y, i64 nrows, i64 p, i64 row0, unsigned lo
 //   times_out (8): generate, standardize (statistics + apply), gram (+ X'y), lanczos + cholesky, iterations, total, 0, 0
 //   aux_out (6): rho, eig estimate, lambda0, scaleY, meanY, total iterations
 int oracle_tall_fit_synth(i64 n, i64 p, unsigned long long seed, float mean_x, float sd_x, int nsig, float noise,
-                          i64 chunk_rows, int nlambda, double lmin_ratio, int maxit, double eps_abs, double eps_rel, double rho,
+                          i64 chunk_rows, int enet, double alpha, double lambda_frac /* > 0: the single lambda = frac * lambda_max */,
+                          int nlambda, double lmin_ratio, int maxit, double eps_abs, double eps_rel, double rho,
                           double* lambda_out, double* beta_out /* (p+1) x nl */, int* niter_out,
                           double* times_out, double* aux_out, float* gram_out /* p x p lower, optional */, float* xy_out /* optional */)
 {
@@ -912,8 +913,12 @@ int oracle_tall_fit_synth(i64 n, i64 p, unsigned long long seed, float mean_x, f
 
     // ---- lambda grid + path (Lasso.cpp:78-124) ------------------------------------------------------------
     TallLasso m(p, XY.data(), eps_abs, eps_rel);
+    if (enet) m.set_enet(alpha);
+    if (lambda_frac > 0) nlambda = 1;
     std::vector<double> lam(nlambda);
-    make_lambda_grid((double)m.lambda0 / (double)n * (double)scaleY, lmin_ratio, nlambda, lam.data());
+    const double lmax = (double)m.lambda0 / (double)n * (double)scaleY;
+    if (lambda_frac > 0) lam[0] = lambda_frac * lmax;
+    else make_lambda_grid(lmax, lmin_ratio, nlambda, lam.data());
     double t_setup = 0, t_iter = 0;
     long long total_it = 0;
     std::vector<float> coef(p);

@@ -4,6 +4,11 @@
 // its vendored Spectra:  SymEigsSolver<Scalar, LARGEST_ALGE>(op, nev=1, ncv=3),
 // init() with the deterministic LCG start vector, compute(maxit=10, tol=0.1).
 //
+// Pinned independently of the product: the library's own Lanczos driver is a sibling of this file (same reading
+// of Spectra, written twice), so this restatement is checked against a third, structurally different one --
+// tests/spectra_numpy.py (matrix form, LAPACK for the 3 x 3 eigenproblem) -- in
+// tests/test_lanczos_independent_cpu.py: 25 matrices, 0-3 implicit restarts, 5e-6 relative.
+//
 // Follows (by reading, not by copying):
 //   /root/reference/src/Spectra/SymEigsSolver.h:201-280  (Lanczos step + re-orthogonalisation)
 //   /root/reference/src/Spectra/SymEigsSolver.h:283-323  (implicit restart)

@@ -200,9 +200,11 @@ def synth_f32(nrows, p, row0=0, seed=123, mean_x=0.0, sd_x=2.0, nsig=100, noise=
 
 
 def tall_fit_synth(n, p, seed=123, mean_x=0.0, sd_x=2.0, nsig=100, noise=1.0, chunk_rows=32768, nlambda=100,
-                   lambda_min_ratio=1e-4, maxit=10000, eps_abs=1e-5, eps_rel=1e-5, rho=-1.0, want_gram=False):
+                   enet=False, alpha=1.0, lambda_frac=0.0, lambda_min_ratio=1e-4, maxit=10000, eps_abs=1e-5, eps_rel=1e-5, rho=-1.0, want_gram=False):
     """admm_lasso(x, y)$penalty(nlambda)$fit() of the reference on the full synthetic design, X streamed in row
     chunks (never resident).  Returns lambda, beta[(p+1) x nl], niter, times (s) and rho/eig/lambda0/scaleY/meanY."""
+    if lambda_frac > 0:
+        nlambda = 1
     lam = np.zeros(nlambda)
     beta = np.zeros((p + 1, nlambda), order="F")
     niter = np.zeros(nlambda, dtype=np.int32)
@@ -212,7 +214,8 @@ def tall_fit_synth(n, p, seed=123, mean_x=0.0, sd_x=2.0, nsig=100, noise=1.0, ch
     xy = np.zeros(p, dtype=np.float32) if want_gram else None
     rc = lib().oracle_tall_fit_synth(
         c_i64(n), c_i64(p), C.c_ulonglong(seed), C.c_float(mean_x), C.c_float(sd_x), C.c_int(nsig), C.c_float(noise),
-        c_i64(chunk_rows), C.c_int(nlambda), C.c_double(lambda_min_ratio), C.c_int(maxit), C.c_double(eps_abs),
+        c_i64(chunk_rows), C.c_int(int(enet)), C.c_double(alpha), C.c_double(lambda_frac),
+        C.c_int(nlambda), C.c_double(lambda_min_ratio), C.c_int(maxit), C.c_double(eps_abs),
         C.c_double(eps_rel), C.c_double(rho), _dp(lam), _dp(beta), _ip(niter), _dp(times), _dp(aux), _fp(G), _fp(xy))
     if rc != 0:
         raise RuntimeError(f"oracle_tall_fit_synth failed rc={rc}")

@@ -1,7 +1,9 @@
-"""bench.py's reference arm measures the CPU iteration phase on a Gram matrix with the full-size design's
-statistics (wishart_problem) instead of forming the 40 GB design.  Check on a size the oracle can do both ways
-that the surrogate reproduces the real design's path: same lambda_max scale, iteration count within a few per cent."""
+"""bench.py's CPU-side pieces (no GPU): the reference arm runs the oracle on the full synthetic design (measured, not
+extrapolated) and prints the contract's JSON line; the parity helpers recover coefficients as DataStd does and flag
+coefficient / support / iteration-count differences."""
+import json
 import os
+import subprocess
 import sys
 
 import numpy as np
@@ -10,28 +12,59 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def test_wishart_surrogate_reproduces_the_iteration_count():
+def test_reference_arm_prints_a_measured_line(tmp_path):
+    env = dict(os.environ, TMPDIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "20000", "--p", "256", "--nlambda", "12",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["steps_measured"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["extrapolated"] is False and cb["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    m = cb["measured_s"]
+    wall = m["standardize"] + m["gram"] + m["lanczos_cholesky"] + m["iterations"]          # generation excluded: X is an input
+    assert abs(line["ms_per_step"] - wall * 1e3) < 1e-6 * wall * 1e3 + 1e-9
+    assert abs(line["value"] - line["niter_path"] / wall) < 1e-9 * line["value"]
+    # the fit is left for the GPU arm to compare with
+    saved = [f for f in os.listdir(tmp_path) if f.startswith("b200admm_ref_tall_n20000_p256_l12")]
+    assert saved
+    z = np.load(os.path.join(tmp_path, saved[0]))
+    assert z["beta"].shape == (257, 12) and int(z["niter"].sum()) == line["niter_path"]
+
+
+def test_rank_other_than_zero_prints_nothing_in_the_reference_arm():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
+                       timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_parity_helpers():
     import bench
-    from oracle import pyoracle as O
-    n, p, nl = 40000, 400, 30
-    rng = np.random.default_rng(3)
-    x = np.asfortranarray((rng.standard_normal((n, p)) * 2.0).astype(np.float32))
-    beta = np.zeros(p, dtype=np.float32)
-    beta[:100] = rng.uniform(size=100)
-    y = (x @ beta + rng.standard_normal(n).astype(np.float32)).astype(np.float32)
-    O.standardize_f32(x, y)
-    G = O.gram_tn_f32(x)
-    xy = (x.T.astype(np.float64) @ y.astype(np.float64)).astype(np.float32)
-    lam0 = float(np.abs(xy).max())
-    grid = np.exp(np.linspace(np.log(lam0), np.log(lam0 * 1e-4), nl))
-    real = O.tall_path_from_gram(G, xy, grid)
-
-    Gs, xys = bench.wishart_problem(n, p, seed=7)
-    lam0s = float(np.abs(xys).max())
-    grids = np.exp(np.linspace(np.log(lam0s), np.log(lam0s * 1e-4), nl))
-    sur = O.tall_path_from_gram(Gs, xys, grids)
-
-    assert abs(lam0s / lam0 - 1.0) < 0.1                                  # same lambda_max up to sampling noise
-    nr, ns = int(real["niter"].sum()), int(sur["niter"].sum())
-    assert abs(ns - nr) <= 0.08 * nr, (nr, ns)
-    assert abs(float(sur["rho"]) / float(real["rho"]) - 1.0) < 0.1
+    rng = np.random.default_rng(0)
+    p = 50
+    z = np.zeros(p, dtype=np.float32)
+    z[[1, 7, 30]] = [0.5, -1.25, 2.0]
+    meanX = rng.normal(size=p).astype(np.float32)
+    scaleX = rng.uniform(0.5, 2, size=p).astype(np.float32)
+    b = bench.recover_f32(z, meanX, scaleX, 3.0, 1.5)
+    assert b.shape == (p + 1,) and (b[1:] != 0).sum() == 3
+    assert np.allclose(b[1:][[1, 7, 30]], z[[1, 7, 30]] / scaleX[[1, 7, 30]] * 1.5, rtol=1e-6)
+    assert np.isclose(b[0], 3.0 - (b[1:] * meanX).sum(), rtol=1e-5)
+    B = np.stack([b, 0.5 * b], axis=1)
+    same = bench.compare_paths(B, B.copy(), np.array([10, 12]), np.array([10, 12]), None, 2e-4, 1e-4)
+    assert same["ok"] and same["max_abs_dbeta"] == 0 and same["support_mismatch"] == 0
+    B2 = B.copy()
+    B2[5, 0] = 0.01                                      # a spurious coefficient outside the band
+    bad = bench.compare_paths(B2, B, np.array([10, 12]), np.array([10, 12]), None, 2e-4, 1e-4)
+    assert not bad["ok"] and bad["support_mismatch_outside_band"] == 1
+    B3 = B.copy()
+    B3[5, 0] = 5e-5                                      # inside the band and the tolerance: reported, not fatal
+    near = bench.compare_paths(B3, B, np.array([10, 12]), np.array([10, 12]), None, 2e-4, 1e-4)
+    assert near["ok"] and near["support_mismatch"] == 1 and near["support_mismatch_outside_band"] == 0
+    slow = bench.compare_paths(B, B, np.array([10, 40]), np.array([10, 12]), None, 2e-4, 1e-4)
+    assert not slow["ok"]

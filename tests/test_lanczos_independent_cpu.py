@@ -1,0 +1,47 @@
+"""The coarse lambda_max estimate (Spectra nev = 1, ncv = 3, maxit 10, tol 0.1) fixes the default rho / gamma and so
+the whole iterate path.  The product's coarse_eig.hpp and the oracle's lanczos.hpp are the same restatement written
+twice, so "rho agrees with the oracle" cannot detect a misreading of Spectra.  This pins the ORACLE's against an
+independent NumPy restatement (tests/spectra_numpy.py: matrix form, LAPACK eigensolver for the 3 x 3 problem) on 25
+matrices, including ones that need 1, 2 and 3 implicit restarts; tests/test_gpu_kernels.py does the same for the
+product's on the device.  Bound: 5e-6 relative (float32 recurrences in different summation orders), identical
+operator-application and restart counts."""
+import numpy as np
+import pytest
+
+import lanczos_cases
+import spectra_numpy as SN
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def test_oracle_lanczos_matches_independent_numpy_restatement(O):
+    restarts = set()
+    n = 0
+    for name, S in lanczos_cases.cases():
+        ev_o, info = O.coarse_eig_f32(S)
+        ev_n, nmat, nrs, conv = SN.coarse_largest_eigenvalue(S)
+        assert info["converged"] == conv == 1, name
+        assert info["nmatvec"] == nmat and info["nrestart"] == nrs, (name, info, nmat, nrs)
+        assert abs(ev_o / ev_n - 1.0) < 5e-6, (name, ev_o, ev_n)
+        true = float(np.linalg.eigvalsh(S.astype(np.float64))[-1])
+        assert 0.45 * true < ev_n <= true * (1 + 1e-5), (name, ev_n, true)      # a coarse estimate from below
+        restarts.add(nrs)
+        n += 1
+    assert n >= 20 and {0, 1, 2, 3} <= restarts, restarts
+
+
+def test_lehmer_start_vector():
+    # SimpleRandom(0): r0 = 1, r1 = 16807, r2 = 282475249, r3 = 1622650073 (the minimal-standard generator)
+    v = SN.simple_random_vec(4, 0)
+    want = np.array([16807, 282475249, 1622650073, 984943658], dtype=np.float64) / 2147483647.0 - 0.5
+    assert np.allclose(v, want.astype(np.float32), rtol=0, atol=1e-7)
+    # 2^31 - 1 is prime and 16807 a primitive root: the split form equals (a r) mod m
+    r = 1
+    for _ in range(1000):
+        r = (16807 * r) % 2147483647
+    w = SN.simple_random_vec(1000, 0)
+    assert np.isclose(w[-1], np.float32(r) / np.float32(2147483647) - np.float32(0.5), atol=1e-7)
