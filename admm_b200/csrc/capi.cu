@@ -18,6 +18,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 namespace b200 {
@@ -342,8 +343,9 @@ void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* k
         const void *a = nullptr, *W = nullptr, *keep = nullptr;
         i64 p = -1, ld = -1;
         unsigned long long kernels = 0;       // kernel nodes in the graph (added to the launch count on every replay)
-        DevBuf<T> work, tmp;
+        DevBuf<T> work, tmp, zt;
         DevBuf<int> info;
+        bool tensor = false;
     };
     static FactorGraph& fg = *new FactorGraph;      // lives until process exit (its buffers go back to the driver with the context)
     const char* genv = getenv("B200ADMM_GRAPH");
@@ -351,17 +353,29 @@ void spd_inverse(cudaStream_t s, T* a, i64 p, i64 ld, T* W, int* info_host, T* k
     const bool hit = use_graph && fg.exec && fg.a == a && fg.W == W && fg.keep == keep_factor && fg.p == p && fg.ld == ld;
     if (!hit) {
         if (fg.exec) { cudaGraphExecDestroy(fg.exec); fg.exec = nullptr; }
-        if (fg.p != p) { fg.work.alloc(chol_work<T>(p)); fg.tmp.alloc(tri_inverse_tmp(p)); }
+        // float32, p >= 512, no factor to hand back: everything on the tensor cores (chol.cu: spd_inverse_tc)
+        const bool tensor = std::is_same<T, float>::value && !keep_factor && spd_inverse_tc_usable(p, ld);
+        if (fg.p != p || fg.ld != ld || fg.tensor != tensor) {
+            fg.work.release(); fg.tmp.release(); fg.zt.release();
+            if (tensor) { fg.work.alloc(spd_tc_work_floats(p)); fg.zt.alloc((size_t)p * (size_t)ld); }
+            else { fg.work.alloc(chol_work<T>(p)); fg.tmp.alloc(tri_inverse_tmp(p)); }
+        }
+        fg.tensor = tensor;
         if (!fg.info.p) fg.info.alloc(1);
         fg.a = a; fg.W = W; fg.keep = keep_factor; fg.p = p; fg.ld = ld;
         cudaGraph_t graph = nullptr;
         const unsigned long long count0 = g_launch_count;
         if (use_graph) CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
         try {
-            chol_lower<T>(s, a, p, ld, fg.work.p, fg.info.p);
-            if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
-            tri_inverse_lower<T>(s, a, p, ld, fg.work.p, W, ld, fg.tmp.p);
-            gram_of_lower<T>(s, W, p, ld, a, ld);
+            if (tensor) {
+                spd_inverse_tc(s, reinterpret_cast<float*>(a), p, ld, reinterpret_cast<float*>(W), reinterpret_cast<float*>(fg.zt.p),
+                               reinterpret_cast<float*>(fg.work.p), fg.info.p);
+            } else {
+                chol_lower<T>(s, a, p, ld, fg.work.p, fg.info.p);
+                if (keep_factor) CUDA_CHECK(cudaMemcpyAsync(keep_factor, a, sizeof(T) * (size_t)ld * (size_t)p, cudaMemcpyDeviceToDevice, s));
+                tri_inverse_lower<T>(s, a, p, ld, fg.work.p, W, ld, fg.tmp.p);
+                gram_of_lower<T>(s, W, p, ld, a, ld);
+            }
         } catch (...) {
             if (use_graph) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); }
             fg.p = -1;
@@ -683,6 +697,17 @@ int b200admm_k_coarse_eig_f32(const void* sm, int64_t n, float* ev_host, int* in
     });
 }
 
+int b200admm_k_gemm_tn_f32(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                           void* c, int64_t ldc, int tile_mode, int klo_mode, int khi_mode, int epi)
+{
+    return fenced([&] {
+        Context& cx = ctx();
+        if (!gemm_tn_tensor(cx.stream, (const float*)a, lda, (const float*)b, ldb, m, n, k, (float*)c, ldc, tile_mode, klo_mode, khi_mode, epi))
+            throw ArgError("tensor-core TN product cannot take this shape (leading dimensions % 4, 16-byte aligned bases, even SM count)");
+        CUDA_CHECK(cudaStreamSynchronize(cx.stream));
+    });
+}
+
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host)
 {
     return fenced([&] {
@@ -695,6 +720,19 @@ int b200admm_k_chol_f32(void* a, int64_t p, int* info_host)
         CUDA_CHECK(cudaStreamSynchronize(c.stream));
         if (info_host) *info_host = h;
     });
+}
+
+// debug / tuning aid, not part of the documented ABI: mean ms per launch of a one-CTA diagonal-block kernel
+extern "C" double b200admm_debug_diag_ms(int mode, int reps, void* a, int64_t lda, void* dinv)
+{
+    double ms = -1;
+    fenced([&] {
+        Context& c = ctx();
+        DevBuf<int> info(1);
+        info.zero(c.stream);
+        ms = diag_kernel_bench(c.stream, mode, reps, (float*)a, lda, (float*)dinv, info.p);
+    });
+    return ms;
 }
 
 int b200admm_k_spd_inverse_f32(void* a, int64_t p, void* work, int* info_host)

@@ -639,6 +639,245 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G,
 }
 
 // =================================================================================================
+// General two-operand form of the CTA-pair TF32 kernel:  C (M x N) op= A' B  for A (K x M) and B (K x N), both
+// column-major (K contiguous: the "TN" product, the only form the K-major tensor-core operands take without a
+// transposing copy).  Same pipeline as gram_pair_kernel (TMA -> hi / lo splitter -> three kind::tf32 products per
+// k-slice -> 128-row TMEM chunks added into fp32 registers), with
+//   * two tensor maps (the Gram kernel reads both operand tiles from one matrix),
+//   * a tile set: the whole nI x nJ grid, or the tiles on and below / on and above the diagonal,
+//   * a K range per tile, in 32-row stages, from which the structurally zero blocks of a triangular operand are
+//     left out (the operand must hold explicit zeros in the part of its diagonal blocks that is not skipped),
+//   * an epilogue: C = acc, C -= acc or C = -acc.
+// It carries the blocked factorisation behind K^-1 = (X'X + rho I)^-1 (chol.cu): rank-128 and rank-1024 updates
+// of the Cholesky factor, the block products of the triangular inverse and K^-1 = Z'Z.
+// =================================================================================================
+struct TnArgs {
+    int tile_mode;     // 0: all nI x nJ tiles (I-major), 1: J <= I, 2: J >= I
+    int nI, nJ, ntiles;
+    int nk;            // K extent in stages of BK rows
+    int klo_mode;      // first stage: 0 -> 0, 1 -> start of block I, 2 -> start of block J, 3 -> start of block max(I, J)
+    int khi_mode;      // end stage:   0 -> nk, 1 -> end of block I, 2 -> end of block J, 3 -> end of block min(I, J)
+    int epi;           // 0: C = acc, 1: C -= acc, 2: C = -acc
+    int M, N;          // valid rows / columns of C
+    long long ldc;
+};
+__device__ __forceinline__ void tn_tile_coords(const TnArgs& a, int t, int& I, int& J)
+{
+    if (a.tile_mode == 0) { I = t / a.nJ; J = t - I * a.nJ; return; }
+    int i = 0;
+    for (;;) {
+        const int cnt = a.tile_mode == 1 ? i + 1 : a.nJ - i;
+        if (t < cnt) break;
+        t -= cnt; i++;
+    }
+    I = i; J = a.tile_mode == 1 ? t : i + t;
+}
+__device__ __forceinline__ void tn_tile_krange(const TnArgs& a, int I, int J, int& k0, int& k1)
+{
+    constexpr int SPB = T2 / BK;                       // stages per 256-row block
+    const int lo = a.klo_mode == 0 ? 0 : (a.klo_mode == 1 ? I : (a.klo_mode == 2 ? J : max(I, J)));
+    const int hi = a.khi_mode == 1 ? I : (a.khi_mode == 2 ? J : min(I, J));
+    k0 = min(lo * SPB, a.nk - 1);
+    k1 = a.khi_mode == 0 ? a.nk : min(a.nk, (hi + 1) * SPB);
+    if (k1 <= k0) k1 = k0 + 1;                         // never empty: the roles below count stages in lock step
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+tn_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C, const TnArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* raw = base;
+    unsigned char* lo = base + P2_RAW * P2_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lo + P2_LO * P2_STAGE);
+    uint64_t* full_raw = bars;                        // [P2_RAW]  local: TMA -> splitter
+    uint64_t* empty_raw = bars + P2_RAW;              // [P2_RAW]  MMA commit (multicast) -> TMA
+    uint64_t* full_lo = bars + 2 * P2_RAW;            // [P2_LO]   leader's: splitters of both CTAs -> MMA
+    uint64_t* empty_lo = full_lo + P2_LO;             // [P2_LO]   MMA commit (multicast) -> splitter
+    uint64_t* tmem_full = empty_lo + P2_LO;           // [2]       MMA commit (multicast) -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;             // [2]       leader's: epilogues of both CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P2_RAW; i++) { mbar_init(smem_u32(full_raw + i), 1); mbar_init(smem_u32(empty_raw + i), 1); }
+        for (int i = 0; i < P2_LO; i++) { mbar_init(smem_u32(full_lo + i), 2 * SPLIT_THREADS); mbar_init(smem_u32(empty_lo + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(tmem_full + i), 1); mbar_init(smem_u32(tmem_empty + i), 2 * EPI_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+
+    if (warp == 0) {
+        // ================================ TMA producer (each CTA, local) ================
+        if (lane == 0) {
+            Ring r;
+            for (int t = pair; t < a.ntiles; t += npairs) {
+                int I, J, k0, k1;
+                tn_tile_coords(a, t, I, J);
+                tn_tile_krange(a, I, J, k0, k1);
+                for (int ks = k0; ks < k1; ks++) {
+                    mbar_wait(smem_u32(empty_raw + r.idx), r.phase ^ 1u);
+                    const uint32_t fb = smem_u32(full_raw + r.idx);
+                    mbar_expect_tx(fb, P2_STAGE);
+                    const uint32_t dst = smem_u32(raw + r.idx * P2_STAGE);
+                    tma_load_2d(dst, &mapA, ks * BK, I * T2 + (int)rank * 128, fb);
+                    tma_load_2d(dst + P2_A_BYTES, &mapB, ks * BK, J * T2 + (int)rank * 128, fb);
+                    r.advance(P2_RAW);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ================
+        if (rank == 0 && lane == 0) {
+            Ring r, q, acc;
+            for (int t = pair; t < a.ntiles; t += npairs) {
+                int I, J, k0, k1;
+                tn_tile_coords(a, t, I, J);
+                tn_tile_krange(a, I, J, k0, k1);
+                for (int ks = k0; ks < k1; ks++) {
+                    const int c = (ks - k0) % CHUNK_STEPS;
+                    if (c == 0) {
+                        mbar_wait_cluster(smem_u32(tmem_empty + acc.idx), acc.phase ^ 1u);
+                        tc_fence_after();
+                    }
+                    mbar_wait_cluster(smem_u32(full_lo + q.idx), q.phase);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(acc.idx * T2);
+                    const uint32_t ra = smem_u32(raw + r.idx * P2_STAGE), la = smem_u32(lo + q.idx * P2_STAGE);
+                    const uint64_t a_hi = umma_desc_k(ra), b_hi = umma_desc_k(ra + P2_A_BYTES);
+                    const uint64_t a_lo = umma_desc_k(la), b_lo = umma_desc_k(la + P2_A_BYTES);
+#pragma unroll
+                    for (int sub = 0; sub < BK / 8; sub++) {
+                        const uint64_t off = (uint64_t)(sub * 32 >> 4);
+                        tc_mma_tf32_pair(d, a_hi + off, b_hi + off, IDESC2, (c > 0 || sub > 0) ? 1u : 0u);
+                        tc_mma_tf32_pair(d, a_lo + off, b_hi + off, IDESC2, 1u);
+                        tc_mma_tf32_pair(d, a_hi + off, b_lo + off, IDESC2, 1u);
+                    }
+                    tc_commit_pair(smem_u32(empty_raw + r.idx));
+                    tc_commit_pair(smem_u32(empty_lo + q.idx));
+                    if (c == CHUNK_STEPS - 1 || ks == k1 - 1) {
+                        tc_commit_pair(smem_u32(tmem_full + acc.idx));
+                        acc.advance(2);
+                    }
+                    r.advance(P2_RAW);
+                    q.advance(P2_LO);
+                }
+            }
+        }
+    } else if (warp >= 3 && warp < 8) {
+        // ================================ hi / lo splitter (each CTA) ==================
+        const int st = threadIdx.x - 96;
+        Ring r, q;
+        for (int t = pair; t < a.ntiles; t += npairs) {
+            int I, J, k0, k1;
+            tn_tile_coords(a, t, I, J);
+            tn_tile_krange(a, I, J, k0, k1);
+            for (int ks = k0; ks < k1; ks++) {
+                mbar_wait(smem_u32(full_raw + r.idx), r.phase);
+                mbar_wait(smem_u32(empty_lo + q.idx), q.phase ^ 1u);
+                const uint32_t src = smem_u32(raw + r.idx * P2_STAGE);
+                const uint32_t dst = smem_u32(lo + q.idx * P2_STAGE);
+#pragma unroll 4
+                for (int e = st; e < P2_STAGE / 16; e += SPLIT_THREADS) {
+                    const uint32_t off = (uint32_t)e * 16u;
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
+                    auto rn = [](uint32_t b) { return (b + 0x1000u) & 0xFFFFE000u; };
+                    uint4 h;
+                    h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
+                    const float lx = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x))));
+                    const float ly = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y))));
+                    const float lz = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z))));
+                    const float lw = __uint_as_float(rn(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w))));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(dst + off), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(src + off), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
+                }
+                fence_proxy_async();
+                mbar_arrive_cluster(smem_u32(full_lo + q.idx), 0);
+                r.advance(P2_RAW);
+                q.advance(P2_LO);
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================ epilogue (each CTA: its 128 rows) =============
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;" ::: "memory");
+        const int quad = warp & 3;
+        const int half = (warp - 8) >> 2;
+        Ring acc;
+        float sum[T2 / 2];
+#pragma unroll
+        for (int c = 0; c < T2 / 2; c++) sum[c] = 0.f;
+        for (int t = pair; t < a.ntiles; t += npairs) {
+            int I, J, k0, k1;
+            tn_tile_coords(a, t, I, J);
+            tn_tile_krange(a, I, J, k0, k1);
+            const int nchunk = (k1 - k0 + CHUNK_STEPS - 1) / CHUNK_STEPS;
+            const int row = I * T2 + (int)rank * 128 + quad * 32 + lane;
+            for (int ch = 0; ch < nchunk; ch++) {
+                mbar_wait_relaxed(smem_u32(tmem_full + acc.idx), acc.phase);
+                tc_fence_after();
+#pragma unroll
+                for (int cg = 0; cg < T2 / 2 / 32; cg++) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc.idx * T2 + half * (T2 / 2) + cg * 32);
+                    tc_ld32(taddr, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; c++) sum[cg * 32 + c] += __uint_as_float(v[c]);
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(smem_u32(tmem_empty + acc.idx), 0);
+                acc.advance(2);
+            }
+            const int col0 = J * T2 + half * (T2 / 2);
+            float* g = C + (size_t)row + (size_t)col0 * a.ldc;
+            if (a.epi == 1) {
+#pragma unroll
+                for (int c0 = 0; c0 < T2 / 2; c0 += 16) {
+                    float old[16];
+#pragma unroll
+                    for (int c = 0; c < 16; c++) old[c] = (row < a.M && col0 + c0 + c < a.N) ? g[(size_t)(c0 + c) * a.ldc] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) {
+                        if (row < a.M && col0 + c0 + c < a.N) g[(size_t)(c0 + c) * a.ldc] = __fsub_rn(old[c], sum[c0 + c]);
+                        sum[c0 + c] = 0.f;
+                    }
+                    asm volatile("" ::: "memory");
+                }
+            } else {
+                const float sgn = a.epi == 2 ? -1.f : 1.f;
+#pragma unroll
+                for (int c = 0; c < T2 / 2; c++) {
+                    if (row < a.M && col0 + c < a.N) g[(size_t)c * a.ldc] = sgn * sum[c];
+                    sum[c] = 0.f;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// =================================================================================================
 // CTA-pair kernel on PRE-SPLIT fp16 operands (tcgen05 kind::f16, twice the TF32 rate, no splitter).
 //
 // For columns of unit scale (DataStd flags 1 and 3: |x| <= sqrt(n), typical |x| ~ 1) an fp16 pair
@@ -1290,6 +1529,47 @@ bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G,
         KERNEL_CHECK();
     }
     return true;
+}
+
+// C (M x N, ldc) op= A' B on the CTA-pair TF32 kernel (see tn_pair_kernel).  A: K x M, B: K x N, column-major with
+// leading dimensions lda / ldb (multiples of 4 floats, 16-byte aligned bases).  Returns false when the shape or the
+// device cannot take it (the caller then uses gemm<float>).
+bool gemm_tn_tensor(cudaStream_t s, const float* A, i64 lda, const float* B, i64 ldb, i64 M, i64 N, i64 K, float* C, i64 ldc,
+                    int tile_mode, int klo_mode, int khi_mode, int epi)
+{
+    if (lda % 4 != 0 || ldb % 4 != 0 || (((uintptr_t)A) & 15) != 0 || (((uintptr_t)B) & 15) != 0) return false;
+    if (M < 1 || N < 1 || K < 1 || (sm_count() % 2 != 0)) return false;
+    if (K >= 2147483647LL - BK || M >= 2147483647LL - T2 || N >= 2147483647LL - T2) return false;
+    const char* kenv = getenv("B200ADMM_GRAM_KERNEL");
+    if (kenv && !strcmp(kenv, "1cta")) return false;
+    TnArgs a;
+    a.tile_mode = tile_mode;
+    a.nI = (int)((M + T2 - 1) / T2); a.nJ = (int)((N + T2 - 1) / T2);
+    if (tile_mode != 0 && a.nI != a.nJ) return false;
+    a.ntiles = tile_mode == 0 ? a.nI * a.nJ : a.nI * (a.nI + 1) / 2;
+    a.nk = (int)((K + BK - 1) / BK);
+    a.klo_mode = klo_mode; a.khi_mode = khi_mode; a.epi = epi;
+    a.M = (int)M; a.N = (int)N; a.ldc = (long long)ldc;
+    CUtensorMap mapA, mapB;
+    make_map(&mapA, A, K, lda, M, 128);
+    make_map(&mapB, B, K, ldb, N, 128);
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+        attr = true;
+    }
+    const int grid = 2 * std::min(a.ntiles, sm_count() / 2);
+    tn_pair_kernel<<<grid, 512, P2_SMEM, s>>>(mapA, mapB, C, a);
+    KERNEL_CHECK();
+    return true;
+}
+
+// upper triangle <- lower triangle of the p x p matrix G
+void mirror_lower_to_upper(cudaStream_t s, float* G, i64 p, i64 ld)
+{
+    dim3 mg((unsigned)((p + 31) / 32), (unsigned)((p + 31) / 32));
+    mirror_lower_kernel<<<mg, 256, 0, s>>>(G, (int)p, (long long)ld);
+    KERNEL_CHECK();
 }
 
 bool gram_tn_tensor_sub(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* C, i64 ld)

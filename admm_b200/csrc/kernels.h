@@ -52,6 +52,20 @@ bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G,
 // part of the diagonal tiles is overwritten with values nobody reads): the rank-n update of the blocked Cholesky.
 // X: n x p column-major, ldx % 4 == 0, p >= 256.  Returns false if the shape is not taken.
 bool gram_tn_tensor_sub(cudaStream_t s, const float* X, i64 n, i64 ldx, i64 p, float* C, i64 ld);
+// General two-operand form on the same CTA-pair 3xTF32 kernel:  C (M x N, ldc) op= A' B,  A: K x M, B: K x N, both
+// column-major (lda, ldb multiples of 4, 16-byte aligned) -- the TN product whose operands are K-major as they are.
+//   tile_mode  TN_TILES_ALL: every 256 x 256 tile; TN_TILES_LOWER: tiles with J <= I; TN_TILES_UPPER: J >= I (M == N)
+//   klo_mode / khi_mode: the K range of tile (I, J) in 256-row blocks -- first block 0 / I / J / max(I, J), one past
+//              the last block = all / I + 1 / J + 1 / min(I, J) + 1 -- so that the zero blocks of a triangular operand
+//              are skipped (its diagonal blocks must hold explicit zeros)
+//   epi        TN_STORE: C = A'B; TN_SUB: C -= A'B; TN_NEG: C = -A'B
+// Returns false if the shape / device cannot take it.
+enum { TN_TILES_ALL = 0, TN_TILES_LOWER = 1, TN_TILES_UPPER = 2 };
+enum { TN_K_ALL = 0, TN_K_I = 1, TN_K_J = 2, TN_K_OUTER = 3 };     // klo: OUTER = max(I, J); khi: OUTER = min(I, J)
+enum { TN_STORE = 0, TN_SUB = 1, TN_NEG = 2 };
+bool gemm_tn_tensor(cudaStream_t s, const float* A, i64 lda, const float* B, i64 ldb, i64 M, i64 N, i64 K, float* C, i64 ldc,
+                    int tile_mode, int klo_mode, int khi_mode, int epi);
+void mirror_lower_to_upper(cudaStream_t s, float* G, i64 p, i64 ld);
 // synchronises `s`; true (and the flag is cleared) if an fp16 split since the last call met |x| > 65000
 bool gram_f16_overflowed(cudaStream_t s);
 
@@ -86,6 +100,13 @@ template <class T> void chol_lower(cudaStream_t s, T* A, i64 p, i64 lda, T* work
 // W (p x p, zero-initialised by the callee) <- L^-1 given the factor in A and chol's `work`
 size_t tri_inverse_tmp(i64 p);      // entries of tri_inverse_lower's `tmp`
 template <class T> void tri_inverse_lower(cudaStream_t s, const T* L, i64 p, i64 lda, const T* work, T* W, i64 ldw, T* tmp);
+// float32, p >= 512: a <- a^-1 (full symmetric) with all O(p^3) work on the tcgen05 3xTF32 kernel (upper-form blocked
+// Cholesky, block inverse with K-range skipping, Z'Z); Z (p x ld) is left holding L^-1, Zt (p x ld) is scratch.
+// Everything is enqueued on `s` (capturable into a CUDA graph); info_dev as in chol_lower.
+size_t spd_tc_work_floats(i64 p);
+bool spd_inverse_tc_usable(i64 p, i64 ld);
+void spd_inverse_tc(cudaStream_t s, float* a, i64 p, i64 ld, float* Z, float* Zt, float* work, int* info_dev);
+double diag_kernel_bench(cudaStream_t s, int mode, int reps, float* A, i64 lda, float* Dinv, int* info);
 // Kinv (p x p, full symmetric) <- W' W
 template <class T> void gram_of_lower(cudaStream_t s, const T* W, i64 p, i64 ldw, T* Kinv, i64 ldk);
 // solve L L' x = b in place for one right-hand side (LAD's get_x; not on the per-iteration path)

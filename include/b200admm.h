@@ -212,6 +212,12 @@ int b200admm_k_gemv_t_f32(const void* a, int64_t m, int64_t ncol, const void* v,
  * SymEigsSolver<float, LARGEST_ALGE>(op, 1, 3).compute(10, 0.1)) of the symmetric float32 matrix s (n x n, full
  * storage, device).  info_host (optional, 3 ints): products with s, restarts, converged flag. */
 int b200admm_k_coarse_eig_f32(const void* s, int64_t n, float* ev_host, int* info_host);
+/* C (M x N, ldc) op= A' B on the tcgen05 3xTF32 CTA-pair kernel; A: K x M, B: K x N, column-major, device.
+ * tile_mode 0 all tiles / 1 on and below / 2 on and above the diagonal (256 x 256 tiles); klo_mode, khi_mode: K range
+ * per tile in 256-row blocks (0 all; 1 block I; 2 block J; 3 max(I, J) resp. min(I, J)); epi 0 C = A'B, 1 C -= A'B,
+ * 2 C = -A'B.  The building block of the blocked factorisation (kernels.h: gemm_tn_tensor). */
+int b200admm_k_gemm_tn_f32(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                           void* c, int64_t ldc, int tile_mode, int klo_mode, int khi_mode, int epi);
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host);                 /* lower, in place */
 int b200admm_k_spd_inverse_f32(void* a, int64_t p, void* work, int* info_host); /* a <- a^-1 (full) */
 /* fused z + u + residual + norms pass of the accelerated loop on vectors of length len

@@ -68,3 +68,11 @@ def test_parity_helpers():
     assert near["ok"] and near["support_mismatch"] == 1 and near["support_mismatch_outside_band"] == 0
     slow = bench.compare_paths(B, B, np.array([10, 40]), np.array([10, 12]), None, 2e-4, 1e-4)
     assert not slow["ok"]
+    # a lambda whose runs stop at different iterations may differ by the stopping rule's slack, one that stops at the
+    # same iteration may not
+    B4 = B.copy()
+    B4[3, 1] += 2e-3
+    apart = bench.compare_paths(B4, B, np.array([10, 13]), np.array([10, 12]), None, 1e-4, 1e-4, p=10000)
+    assert apart["ok"] and apart["max_abs_dbeta_where_niter_equal"] == 0
+    same = bench.compare_paths(B4, B, np.array([10, 12]), np.array([10, 12]), None, 1e-4, 1e-4, p=10000)
+    assert not same["ok"]

@@ -88,7 +88,7 @@ def test_gemv_t(K, torch):
         assert np.abs(out.cpu().numpy() - ref).max() < 2e-6 * np.sqrt(m) * 3
 
 
-@pytest.mark.parametrize("p", [64, 128, 129, 500, 1000])
+@pytest.mark.parametrize("p", [64, 128, 129, 500, 1000, 1300, 2100, 4352])
 def test_cholesky_and_spd_inverse(K, torch, p):
     rng = np.random.default_rng(p)
     x = rng.normal(size=(4 * p, p))
@@ -268,3 +268,47 @@ def test_product_coarse_eig_matches_independent_numpy_restatement():
         restarts.add(nrs)
     print("\n[parity] product Lanczos vs independent NumPy restatement: worst relative difference %.2e over 25 matrices" % worst)
     assert {0, 1, 2, 3} <= restarts
+
+
+@pytest.mark.parametrize("M,N,Kd,tile_mode,klo,khi,epi", [
+    (700, 900, 300, 0, 0, 0, 0),        # rectangle, ragged everywhere, store
+    (512, 1024, 128, 0, 0, 0, 1),       # rank-128 update: C -= A'B
+    (1000, 1000, 1030, 2, 0, 0, 1),     # tiles on and above the diagonal, subtract (Cholesky trailing update)
+    (1100, 600, 600, 0, 2, 0, 0),       # B lower triangular: K from block J on
+    (900, 520, 900, 0, 0, 1, 2),        # A upper triangular: K up to block I; C = -A'B
+    (1300, 1300, 1300, 1, 3, 0, 0),     # Z'Z with Z lower triangular: tiles below the diagonal, K from max(I, J)
+])
+def test_tensor_core_tn_product(K, torch, M, N, Kd, tile_mode, klo, khi, epi):
+    """tn_pair_kernel (3xTF32, CTA pairs) against float64: every tile set, K-range rule and epilogue the blocked
+    factorisation uses.  Bound: 4e-6 * sqrt(K) * max|A| max|B| (fp32-accurate accumulation)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + Kd)
+    lda, ldb, ldc = (Kd + 3) // 4 * 4 + 4, (Kd + 3) // 4 * 4, (M + 3) // 4 * 4
+    A = torch.zeros((M, lda), device="cuda")            # column-major K x M: row i of this tensor = column i of A
+    B = torch.zeros((N, ldb), device="cuda")
+    A[:, :Kd] = torch.randn((M, Kd), device="cuda", generator=g)
+    B[:, :Kd] = torch.randn((N, Kd), device="cuda", generator=g)
+    ki = torch.arange(Kd, device="cuda")
+    if klo == 2:                                        # B(k, j) = 0 for k < j
+        B[:, :Kd] *= (ki[None, :] >= torch.arange(N, device="cuda")[:, None]).float()
+    if khi == 1:                                        # A(k, i) = 0 for k > i
+        A[:, :Kd] *= (ki[None, :] <= torch.arange(M, device="cuda")[:, None]).float()
+    if klo == 3:                                        # both lower triangular (one matrix Z)
+        A[:, :Kd] *= (ki[None, :] >= torch.arange(M, device="cuda")[:, None]).float()
+        B = A
+        ldb = lda
+    C0 = torch.randn((N, ldc), device="cuda", generator=g)
+    Cd = C0.clone()
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_gemm_tn_f32(A.data_ptr(), lda, B.data_ptr(), ldb, M, N, Kd, Cd.data_ptr(), ldc, tile_mode, klo, khi, epi))
+    prod = (B[:, :Kd].double() @ A[:, :Kd].double().t())            # (N, M): entry (j, i) = C(i, j)
+    want = {0: prod, 1: C0[:, :M].double() - prod, 2: -prod}[epi]
+    got = Cd[:, :M].double()
+    ii = torch.arange(M, device="cuda")[None, :] // 256
+    jj = torch.arange(N, device="cuda")[:, None] // 256
+    mask = {0: torch.ones_like(prod, dtype=torch.bool), 1: jj <= ii, 2: jj >= ii}[tile_mode]
+    err = ((got - want).abs() * mask).max().item()
+    assert err < 4e-6 * np.sqrt(Kd) * 16, err
+    # tiles outside the requested set and the padding rows of C are untouched
+    assert torch.equal(Cd[:, M:], C0[:, M:])
+    if tile_mode != 0:
+        assert torch.equal(Cd[:, :M][~mask], C0[:, :M][~mask])
