@@ -71,7 +71,7 @@ def test_parity_helpers():
     # a lambda whose runs stop at different iterations may differ by the stopping rule's slack, one that stops at the
     # same iteration may not
     B4 = B.copy()
-    B4[3, 1] += 2e-3
+    B4[2, 1] += 2e-3
     apart = bench.compare_paths(B4, B, np.array([10, 13]), np.array([10, 12]), None, 1e-4, 1e-4, p=10000)
     assert apart["ok"] and apart["max_abs_dbeta_where_niter_equal"] == 0
     same = bench.compare_paths(B4, B, np.array([10, 12]), np.array([10, 12]), None, 1e-4, 1e-4, p=10000)
