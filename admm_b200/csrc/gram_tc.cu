@@ -1078,6 +1078,7 @@ __global__ void __launch_bounds__(256) xty_reduce_kernel(const float* __restrict
 // does not depend on how many tiles a launch covers (820 tiles over 74 pairs used to cost 12 rounds for
 // 11.08 rounds of work, and a 40-tile panel a whole round).
 constexpr int H_SLICES = 24;
+constexpr int H_SYNC = 8;                           // stages between two progress checks of the producers (power of two)
 struct HWork {
     int ntiles, npairs, rounds, tail, per_tile;   // tail tiles are shared by per_tile pairs each (0: no tail)
     int nslices, nch;                             // canonical slices per tile, chunks per tile
@@ -1130,7 +1131,7 @@ __host__ __device__ __forceinline__ int h_slice_chunk0(const HWork& w, int s) { 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H_THREADS, 1)
 gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ G, int p, long long ld, int nk, int I0, int ntiles,
-                   float* __restrict__ scratch, int* __restrict__ counters, int slice_major)
+                   float* __restrict__ scratch, int* __restrict__ counters, int slice_major, int* __restrict__ prog, int lead)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1167,14 +1168,42 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
 
     if (warp == 0) {
         // ================================ TMA producer (each CTA) =======================
-        if (lane == 0) {
-            Ring r;
-            HItem it;
-            for (int i = 0; h_item(W, pair, i, it); i++) {
-                int I, J;
-                pair_tile_coords(it.tile, I0, I, J);
-                const int ks0 = h_slice_chunk0(W, it.s0) * CHUNK_STEPS, ks1 = min(nk, h_slice_chunk0(W, it.s1) * CHUNK_STEPS);
-                for (int ks = ks0; ks < ks1; ks++) {
+        // Lock step (slice-major full rounds only): the 74 CTA pairs of a round share ~35 operand panels, but the reuse
+        // only happens in the 126 MB L2 if the pairs read the same rows at about the same time (ncu, profiles/r1s: 1.18 TB
+        // of DRAM reads for a 40 GB operand array, L2 hit rate 36 %, a third of the power budget).  Every H_SYNC stages
+        // the leader publishes the pair's stage count and both producers hold back while they are more than `lead` stages
+        // ahead of the slowest pair.  The wait is bounded: a pair that cannot see progress (a CTA pair not resident, e.g.
+        // under MPS) stops throttling for the rest of the launch instead of hanging.
+        Ring r;
+        HItem it;
+        int gstage = 0;
+        const bool can_throttle = slice_major && prog != nullptr && lead > 0;
+        bool throttle = can_throttle;
+        const int nfull = W.rounds * W.nslices;
+        for (int i = 0; h_item(W, pair, i, it); i++) {
+            int I, J;
+            pair_tile_coords(it.tile, I0, I, J);
+            const int ks0 = h_slice_chunk0(W, it.s0) * CHUNK_STEPS, ks1 = min(nk, h_slice_chunk0(W, it.s1) * CHUNK_STEPS);
+            const bool full_item = i < nfull;
+            if (can_throttle && i == nfull && rank == 0 && lane == 0)     // full rounds done: do not hold the others back
+                asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(prog + pair), "r"(0x3fffffff) : "memory");
+            for (int ks = ks0; ks < ks1; ks++) {
+                if (throttle && full_item && (gstage & (H_SYNC - 1)) == 0) {
+                    if (rank == 0 && lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(prog + pair), "r"(gstage) : "memory");
+                    for (int spin = 0;; spin++) {
+                        int m = 0x7fffffff;
+                        for (int q = lane; q < npairs; q += 32) {
+                            int v;
+                            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog + q) : "memory");
+                            m = min(m, v);
+                        }
+                        m = __reduce_min_sync(0xffffffffu, m);
+                        if (gstage - m <= lead) break;
+                        if (spin > 4000) { throttle = false; break; }
+                        __nanosleep(100);
+                    }
+                }
+                if (lane == 0) {
                     mbar_wait(smem_u32(empty + r.idx), r.phase ^ 1u);
                     const uint32_t fb = mapa_rank(smem_u32(full + r.idx), 0);      // the leader's barrier counts both CTAs' bytes
                     if (rank == 0) mbar_expect_tx(smem_u32(full + r.idx), 2 * P2_STAGE);
@@ -1182,10 +1211,14 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
                     // box (cb, ks) of the blocked operand: rows ((cb * nk + ks) * 128 ...) of a dense [rows][64 halves] array
                     tma_load_2d_pair(dst, &map, 0, ((2 * I + (int)rank) * nk + ks) * 128, fb);
                     tma_load_2d_pair(dst + P2_A_BYTES, &map, 0, ((2 * J + (int)rank) * nk + ks) * 128, fb);
-                    r.advance(H_STAGES);
                 }
+                __syncwarp();
+                r.advance(H_STAGES);
+                gstage++;
             }
         }
+        if (can_throttle && rank == 0 && lane == 0)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(prog + pair), "r"(0x3fffffff) : "memory");
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA only) ================
         if (rank == 0 && lane == 0) {
@@ -1520,7 +1553,17 @@ bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G,
         // tile-major, SM clock under the power cap 997 against 930 MHz; results bit-identical); "tile" reverts
         const char* oenv = getenv("B200ADMM_GRAM_ORDER");
         const int slice_major = (oenv && !strcmp(oenv, "tile")) ? 0 : 1;
-        gram_pair_h_kernel<<<2 * npairs, H_THREADS, H_SMEM, s>>>(map, G, (int)p, (long long)ld, (int)nk, I0, ntiles, scratch, counters, slice_major);
+        // lock step of the pairs' producers (see the kernel): lead in stages, B200ADMM_GRAM_LEAD=0 switches it off
+        static int* prog = nullptr;
+        if (!prog) CUDA_CHECK(cudaMalloc(&prog, sizeof(int) * 256));
+        static int lead = -1;
+        if (lead < 0) {
+            const char* lenv = getenv("B200ADMM_GRAM_LEAD");
+            lead = lenv ? atoi(lenv) : 32;
+        }
+        if (slice_major && lead > 0) CUDA_CHECK(cudaMemsetAsync(prog, 0, sizeof(int) * 256, s));
+        gram_pair_h_kernel<<<2 * npairs, H_THREADS, H_SMEM, s>>>(map, G, (int)p, (long long)ld, (int)nk, I0, ntiles, scratch, counters, slice_major,
+                                                                 prog, lead);
         KERNEL_CHECK();
     }
     if (mirror) {

@@ -366,6 +366,55 @@ def compare_paths(bg, bc, ng, nc, lam_std, tol_rel, band_rel, p=None, eps_abs=1e
     return res
 
 
+def trace_rel_diff(tg, tc):
+    """Largest relative difference of two iteration traces; entries that are exactly zero in both (the dual residual
+    of a first iteration) count as equal."""
+    tg, tc = np.asarray(tg, dtype=np.float64), np.asarray(tc, dtype=np.float64)
+    d = np.abs(tg - tc) / np.maximum(np.abs(tc), 1e-300)
+    d[(tg == 0) & (tc == 0)] = 0.0
+    return d.max() if d.size else 0.0
+
+
+def align_traces(ta, tb, rtol):
+    """Align two FADMM iteration traces (rows = eps_primal, resid_primal, eps_dual, resid_dual, rho) modulo "stutter"
+    rows: an iteration that took the restart branch while z stood still repeats the previous one (dual residual exactly
+    0, primal residual unchanged) and the run continues as the other run shifted by one row.  Returns the number of
+    leading rows equal in both (`prefix`), matched row pairs, skipped (stutter) rows of either trace, the largest
+    relative difference over the matched pairs, whether all of tb was consumed, and the index of ta's last matched row."""
+    ta, tb = np.asarray(ta, dtype=np.float64), np.asarray(tb, dtype=np.float64)
+
+    def stutter(t, k):
+        return k > 0 and t[k][3] == 0.0 and abs(t[k][1] - t[k - 1][1]) <= rtol * abs(t[k - 1][1])
+    i = j = matched = 0
+    prefix, in_prefix, max_rel, last_a = 0, True, 0.0, -1
+    sk_a, sk_b = [], []
+    while i < len(ta) and j < len(tb):
+        d = float(trace_rel_diff(ta[i], tb[j]))
+        if d <= rtol:
+            matched += 1
+            max_rel = max(max_rel, d)
+            last_a = i
+            if in_prefix and i == j:
+                prefix += 1
+            i += 1
+            j += 1
+            continue
+        in_prefix = False
+        if stutter(ta, i):
+            sk_a.append(i)
+            i += 1
+        elif stutter(tb, j):
+            sk_b.append(j)
+            j += 1
+        else:
+            break
+    while j < len(tb) and stutter(tb, j):                 # trailing stutter rows of tb leave its state where it was
+        sk_b.append(j)
+        j += 1
+    return {"prefix": prefix, "matched": matched, "skipped_a": sk_a, "skipped_b": sk_b, "max_rel": max_rel, "ok": bool(j == len(tb)),
+            "last_a": last_a}
+
+
 def gram_spot_check(env, Xd, n_local, cap, k=100):
     """k x k Gram entries of the captured matrix against float64 dot products of the standardised generated columns
     (torch float64 on the GPU as the checker).  Single-rank only (the columns must be whole)."""
@@ -850,35 +899,50 @@ def run_lad_bp(args, which):
             cores = host_threads()
             btn = O.use_openblas(cores)
             O.omp_threads(cores)
-            nit_s = 20
-            with K.trace(which=0, cap=nit_s + 5) as tr:
-                fs = fit_device(maxit=nit_s)
+            nit_s, extra = 20, 6
+            with K.trace(which=0, cap=nit_s + extra + 5) as tr:
+                fs = fit_device(maxit=nit_s + extra)
             xh = Xd.cpu().numpy().T                                  # (n, p), Fortran-ordered view of the (p, n) copy
             yh = yd.cpu().numpy()
             t0 = time.perf_counter()
             o = (O.lad(xh, yh, maxit=nit_s, trace_cap=nit_s + 5) if which == "lad" else O.bp(xh, yh, maxit=nit_s, trace_cap=nit_s + 5))
             wall = time.perf_counter() - t0
-            # LAD: the whole prefix.  BP: the rows before the restart rule's knife edge only -- while z = 0 the x-update
-            # returns the same point every iteration, `c < 0.999 c_old` compares a number with 0.999 * (itself / 0.999)
-            # and is decided by the last bit of |r|^2 (tests/test_gpu_parity_midsize.py::test_bp_n500_p5000) -- plus an
-            # optimality certificate of the converged GPU solution: feasible and |beta|_1 <= |planted signal|_1
-            rows = nit_s if which == "lad" else 2
-            tg, tc = tr.rows[:rows], o["trace"][:rows]
-            rel = float(np.abs(tg / np.where(tc == 0, 1, tc) - 1).max())
-            par = {"checker": "CPU oracle on the same float64 matrix (maxit = %d in both): per-iteration (eps, residuals, rho) of the first %d iterations"
-                              % (nit_s, rows), "trace_rows_compared": rows, "trace_max_rel_diff": rel,
-                   "niter_gpu": int(fs.niter), "niter_cpu": int(o["niter"])}
+            # Both solvers start with a run of iterations in which z does not move; the x-update then returns the same point
+            # and the restart rule `c < 0.999 c_old` (src/FADMMBase.h:243) compares a number with 0.999 * (itself / 0.999) --
+            # decided by the last bit of |r|^2, i.e. by the summation order of a norm.  A run that takes the restart branch
+            # repeats the iteration (a "stutter" row: dual residual exactly 0, primal residual unchanged) and is then the
+            # other run shifted by one iteration (measured at n = 5e5 x p = 5e3: all 15 later rows agree to 1e-14 after the
+            # shift, profiles/r2i_lad_bp_trace_forensics.log).  So: rows before the first such decision must agree to 1e-9,
+            # the traces must align modulo stutter rows, and (LAD) the coefficients at the aligned iteration must agree.
+            # BP's rho balancing depends on the iteration INDEX (i > 5, src/FADMMBase.h:250), so its shifted runs part for
+            # good; there the converged GPU solution is certified instead (feasible within what the stopping rule allows,
+            # l1 norm not above the planted signal's).
+            tc = o["trace"][:min(int(o["niter"]), nit_s)]
+            al = align_traces(tr.rows, tc, 1e-9)
+            par = {"checker": "CPU oracle on the same float64 matrix, first %d iterations: per-iteration (eps, residuals, rho) aligned modulo "
+                              "restart-rule stutter rows" % nit_s,
+                   "trace_rows_cpu": int(len(tc)), "rows_equal_before_first_knife_edge": al["prefix"], "rows_aligned": al["matched"],
+                   "gpu_stutter_rows": al["skipped_a"], "cpu_stutter_rows": al["skipped_b"], "trace_max_rel_diff_aligned": al["max_rel"],
+                   "aligned_to_the_end": al["ok"]}
             if which == "lad":
-                db = float(np.abs(fs.beta - o["beta"]).max())
-                par.update({"max_abs_dbeta": db, "beta_inf": float(np.abs(o["beta"]).max())})
-                par["ok"] = bool(rel < 1e-6 and db < 1e-7 * max(1.0, par["beta_inf"]) and par["niter_gpu"] == par["niter_cpu"])
+                par["ok"] = False
+                if al["ok"] and al["last_a"] >= 0:
+                    f2 = fit_device(maxit=al["last_a"] + 1)
+                    db = float(np.abs(f2.beta - o["beta"]).max())
+                    par.update({"gpu_iterations_at_cpu_iteration_%d" % len(tc): al["last_a"] + 1, "max_abs_dbeta": db,
+                                "beta_inf": float(np.abs(o["beta"]).max())})
+                    par["ok"] = bool(al["prefix"] >= 3 and al["max_rel"] < 1e-9 and db < 1e-7 * max(1.0, par["beta_inf"]))
             else:
                 bfull = torch.from_numpy(np.asarray(f.beta.todense())[:, 0]).cuda()
-                feas = float((Xd.t() @ bfull - yd).abs().max() / yd.abs().max())
+                res2 = float((Xd.t() @ bfull - yd).norm())
+                eps_pri = (p ** 0.5) * 1e-4 + 1e-4 * float(bfull.norm())
+                bound = 1.1 * (n ** 0.5 + p ** 0.5) * eps_pri               # |A (z - x)| <= |A|_2 |z - x|, |A|_2 ~ sqrt(n) + sqrt(p)
                 l1, l1_true = float(bfull.abs().sum()), float(bt.abs().sum())
-                par.update({"converged_fit": {"feasibility_rel_inf": feas, "l1_norm": l1, "l1_norm_planted_signal": l1_true,
+                par.update({"converged_fit": {"residual_2norm": res2, "residual_bound_from_stopping_rule": bound,
+                                              "residual_rel_inf": float((Xd.t() @ bfull - yd).abs().max() / yd.abs().max()),
+                                              "l1_norm": l1, "l1_norm_planted_signal": l1_true,
                                               "max_abs_err_vs_planted": float((bfull - bt).abs().max()), "niter": nit}})
-                par["ok"] = bool(rel < 1e-7 and feas < 5e-3 and l1 <= l1_true * (1 + 1e-3) and nit <= args.maxit)
+                par["ok"] = bool(al["prefix"] >= 2 and res2 <= bound and l1 <= l1_true * (1 + 1e-3) and nit <= args.maxit)
             ok = par["ok"]
             line["parity"] = par
             line["cpu_baseline"] = {"value": nit_s / wall, "unit": UNIT_FIT, "cores": cores, "kind": "port",

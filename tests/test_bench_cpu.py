@@ -76,3 +76,38 @@ def test_parity_helpers():
     assert apart["ok"] and apart["max_abs_dbeta_where_niter_equal"] == 0
     same = bench.compare_paths(B4, B, np.array([10, 12]), np.array([10, 12]), None, 1e-4, 1e-4, p=10000)
     assert not same["ok"]
+
+
+def test_trace_rel_diff_treats_common_zeros_as_equal():
+    import bench
+    a = np.array([[7.07e-3, 2.2347, 7.07e-3, 0.0, 1.0], [7.29e-3, 2.2347, 7.29e-3, 0.5, 1.0]])
+    assert bench.trace_rel_diff(a, a.copy()) == 0.0                 # the first iteration's dual residual is exactly 0 in both
+    b = a.copy()
+    b[1, 3] *= 1 + 1e-6
+    assert abs(bench.trace_rel_diff(b, a) - 1e-6) < 1e-9
+    c = a.copy()
+    c[0, 3] = 1e-3                                                  # zero in one trace only: a real difference
+    assert bench.trace_rel_diff(c, a) > 1.0
+
+
+def test_align_traces_modulo_stutter_rows():
+    """A run that takes the restart branch while z stands still repeats the iteration; the traces are then shifts of
+    each other (measured on the GPU at LAD n = 5e5 x p = 5e3)."""
+    import bench
+    base = np.array([[0.063, 27.308, 0.0316, 0.0, 1.0],
+                     [0.063, 27.308, 0.0343, 0.0, 1.0],
+                     [0.063, 27.300, 0.0370, 0.324, 1.0],
+                     [0.063, 26.990, 0.0398, 2.661, 1.0],
+                     [0.063, 25.272, 0.0425, 8.610, 1.0],
+                     [0.063, 22.183, 0.0456, 15.08, 1.0]])
+    same = bench.align_traces(base, base.copy(), 1e-9)
+    assert same["ok"] and same["prefix"] == 6 and same["matched"] == 6 and same["skipped_a"] == [] and same["last_a"] == 5
+    stut = np.insert(base, 3, [0.063, 27.300, 0.0398, 0.0, 1.0], axis=0)       # a stutter after row 2
+    a = bench.align_traces(stut, base, 1e-9)
+    assert a["ok"] and a["prefix"] == 3 and a["matched"] == 6 and a["skipped_a"] == [3] and a["last_a"] == 6
+    b = bench.align_traces(base, stut[:6], 1e-9)                               # the other way round, tb cut after 6 rows
+    assert b["ok"] and b["skipped_b"] == [3] and b["matched"] == 5 and b["last_a"] == 4
+    wrong = base.copy()
+    wrong[4, 1] *= 1.001
+    c = bench.align_traces(wrong, base, 1e-9)
+    assert not c["ok"] and c["prefix"] == 4
