@@ -411,6 +411,318 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
         for (int q = 0; q < 8; q++) a.prof[q] = pf[q];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-GPU form that reads ONE TRIANGLE of the symmetric K^-1 per iteration (2 p^2 bytes instead of 4 p^2).
+//
+// Row i of K^-1 is used up to the diagonal only:  K(i, j), j <= i, serves the dot product of row i (x_i += K(i, j) rhs_j)
+// AND, by symmetry, row j's product (x_j += K(i, j) rhs_i, j < i).  The second contribution belongs to a row that another
+// CTA owns, so phase [A] ends with per-CTA partial vectors and a grid barrier:
+//   [A] CTA c streams the lower-triangle part of its rows.  Rows are folded -- CTA c owns the "top" rows [t0, t1) and the
+//       "bottom" rows [p - t1, p - t0): every folded pair has p + 1 entries, so all CTAs stream the same number of bytes.
+//       Thread t owns the columns 4 (t + 512 s) .. + 3 of every 2048-column stripe s: the column sums (the transposed
+//       contributions) accumulate in the thread's own slots of a shared-memory vector -- no atomics, fixed order -- and the
+//       row sums are reduced across the warp eight rows at a time by a 9-shuffle butterfly, then across the 16 warps.
+//       The CTA stores its partial vector part[c][0 .. p) to global memory (L2-resident: G x p floats).
+//   ---- grid barrier ----
+//   [B] own rows: x_i = (row sum) + sum_c part[c][i] in CTA order (eight threads per row, fixed tree), then the prox, the
+//       residual, the dual update and the six partial norms exactly as in tall_path_kernel.
+//   ---- grid barrier ----   [C] as in tall_path_kernel.
+// Everything is summed in a fixed order: runs are bit-reproducible; against tall_path_kernel only the summation order of
+// the K^-1 product differs.  Needs 2 p floats of shared memory (rhs + column sums): p <= ~25 000; row-sharded runs keep
+// tall_path_kernel (their exchange is per row block).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TRI_ROWS = 8;                 // rows per group (loads in flight per thread)
+constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe
+
+// v[0..7] per lane -> the lanes with (lane & 3) == 0 return the warp total of row ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+__device__ __forceinline__ float butterfly8(float (&v)[TRI_ROWS], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float send = h16 ? v[k] : v[k + 4];
+        const float keep = h16 ? v[k + 4] : v[k];
+        v[k] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float send = h8 ? v[k] : v[k + 2];
+        const float keep = h8 ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    {
+        const float send = h4 ? v[0] : v[1];
+        const float keep = h4 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 2);
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+    return v[0];
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathArgs a, int vrows_per_cta, int ld)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* rhs = smem;                                   // ld floats
+    float* acc = smem + ld;                              // ld floats: column sums of this CTA's rows
+    float* s_dot = acc + ld;                             // [TP_WARPS][2 * vpad]: per-warp row sums
+    const int vpad = (vrows_per_cta + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
+    float* xown = s_dot + TP_WARPS * 2 * vpad;           // [2 * vpad]: row sums of the own rows
+    __shared__ double s_sum[NSUM];
+    __shared__ float s_red[TP_WARPS][NSUM];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int p = a.p;
+    const int V = (p + 1) / 2;                           // folded rows: v <-> rows v and p - 1 - v
+    const int t0 = min(V, cta * vrows_per_cta), t1 = min(V, t0 + vrows_per_cta);
+    const int b0 = max(p - t1, t1), b1 = p - t0;         // bottom rows (the middle row of an odd p belongs to the top block)
+    const int nT = t1 - t0, nB = max(0, b1 - b0);
+    const int nown = nT + nB;
+    const int nvec = ld / 4;
+    auto own_row = [&](int r) -> int { return r < nT ? t0 + r : b0 + (r - nT); };
+    auto is_own = [&](int i) -> bool { return (i >= t0 && i < t1) || (i >= b0 && i < b1); };
+
+    auto zb = [&](int i) -> float* { return a.state + (size_t)i * ld; };
+    auto yb = [&](int i) -> float* { return a.state + (size_t)(3 + i) * ld; };
+    float* adj_z = a.state + 6 * (size_t)ld;
+    float* adj_y = a.state + 7 * (size_t)ld;
+    float* partials = a.state + 8 * (size_t)ld;          // [2][G][PART_STRIDE]
+    float* part = a.tri_part;                            // [G][ld]
+
+    const double rho = a.rho;
+    const float frho = (float)rho;
+    const double sqrt_p = sqrt((double)p);
+    double sx2 = 0.0, sz2 = 0.0, sy2 = 0.0;
+    double adj_a = 1.0, adj_c = 9999.0;
+    int cur = 0;
+    unsigned long long nbar = 0;
+    unsigned git = 0;
+    unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    for (int k = 0; k < a.nl; k++) {
+        const float lambda = (float)a.lambdas[k];
+        const ProxParams prox = make_prox(a.enet, lambda, rho, a.alpha);
+        const bool tracing = (a.trace != nullptr) && (k == a.trace_lambda);
+
+        if (k == 0)
+        for (int v = tid; v < nvec; v += TP_THREADS) {
+            const float4 xy = __ldg(reinterpret_cast<const float4*>(a.XY) + v);
+            const float4 ay = ldcg4(adj_y + 4 * v), az = ldcg4(adj_z + 4 * v);
+            float4 o;
+            o.x = (float)((double)__fsub_rn(xy.x, ay.x) + rho * (double)az.x);
+            o.y = (float)((double)__fsub_rn(xy.y, ay.y) + rho * (double)az.y);
+            o.z = (float)((double)__fsub_rn(xy.z, ay.z) + rho * (double)az.z);
+            o.w = (float)((double)__fsub_rn(xy.w, ay.w) + rho * (double)az.w);
+            reinterpret_cast<float4*>(rhs)[v] = o;
+        }
+        __syncthreads();
+
+        int niter = a.maxit + 1;
+        for (int it = 0; it < a.maxit; it++, git++) {
+            const int nxt = (cur + 1) % 3;
+            const long long tA0 = clock64();
+            const double eps_primal = fmax((double)sqrtf((float)sx2), (double)sqrtf((float)sz2)) * a.eps_rel + sqrt_p * a.eps_abs;
+            const double eps_dual = (double)sqrtf((float)sy2) * a.eps_rel + sqrt_p * a.eps_abs;
+
+            // ---- [A] lower-triangle sweep of the own rows --------------------------------------------
+            for (int v = tid; v < nvec; v += TP_THREADS) reinterpret_cast<float4*>(acc)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool rev = a.snake && (git & 1u);
+            const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS;
+            for (int gg = 0; gg < ngT + ngB; gg++) {
+                const int g = rev ? (ngT + ngB - 1 - gg) : gg;
+                const bool bottom = g >= ngT;
+                const int g0 = (bottom ? g - ngT : g) * TRI_ROWS;              // first row of the group within its block
+                const int blk0 = bottom ? b0 : t0, blkn = bottom ? nB : nT;
+                const int i0 = blk0 + g0;                                      // smallest row of the group
+                const int nr = min(TRI_ROWS, blkn - g0);
+                const int imax = i0 + nr - 1;
+                float d[TRI_ROWS], ri[TRI_ROWS];
+#pragma unroll
+                for (int r = 0; r < TRI_ROWS; r++) { d[r] = 0.f; ri[r] = r < nr ? rhs[i0 + r] : 0.f; }
+                const float* kbase = a.Kinv + (size_t)i0 * ld;
+                for (int c4 = tid; 4 * c4 <= imax; c4 += TP_THREADS) {
+                    const int j0 = 4 * c4;
+                    float4 q[TRI_ROWS];
+#pragma unroll
+                    for (int r = 0; r < TRI_ROWS; r++)
+                        q[r] = (r < nr && j0 <= i0 + r) ? ld_stream_f4(reinterpret_cast<const float4*>(kbase + (size_t)r * ld) + c4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 rj = reinterpret_cast<const float4*>(rhs)[c4];
+                    float4 av = reinterpret_cast<float4*>(acc)[c4];
+                    if (j0 + 3 < i0) {
+                        // all four columns lie strictly below the diagonal for every row of the group
+#pragma unroll
+                        for (int r = 0; r < TRI_ROWS; r++) {
+                            d[r] = fmaf(q[r].x, rj.x, d[r]); d[r] = fmaf(q[r].y, rj.y, d[r]);
+                            d[r] = fmaf(q[r].z, rj.z, d[r]); d[r] = fmaf(q[r].w, rj.w, d[r]);
+                            av.x = fmaf(q[r].x, ri[r], av.x); av.y = fmaf(q[r].y, ri[r], av.y);
+                            av.z = fmaf(q[r].z, ri[r], av.z); av.w = fmaf(q[r].w, ri[r], av.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < TRI_ROWS; r++) {
+                            const int i = i0 + r;                              // rows beyond nr were loaded as zeros
+                            const float qx = j0 <= i ? q[r].x : 0.f, qy = j0 + 1 <= i ? q[r].y : 0.f;
+                            const float qz = j0 + 2 <= i ? q[r].z : 0.f, qw = j0 + 3 <= i ? q[r].w : 0.f;
+                            d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
+                            d[r] = fmaf(qz, rj.z, d[r]); d[r] = fmaf(qw, rj.w, d[r]);
+                            av.x = fmaf(j0 < i ? qx : 0.f, ri[r], av.x); av.y = fmaf(j0 + 1 < i ? qy : 0.f, ri[r], av.y);
+                            av.z = fmaf(j0 + 2 < i ? qz : 0.f, ri[r], av.z); av.w = fmaf(j0 + 3 < i ? qw : 0.f, ri[r], av.w);
+                        }
+                    }
+                    reinterpret_cast<float4*>(acc)[c4] = av;
+                }
+                const float tot = butterfly8(d, lane);
+                if ((lane & 3) == 0) {
+                    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    s_dot[warp * 2 * vpad + (bottom ? vpad : 0) + g0 + r] = tot;
+                }
+            }
+            // the CTA's partial column sums -> global (every thread stores the slots it owns)
+            {
+                float4* dst = reinterpret_cast<float4*>(part + (size_t)cta * ld);
+                for (int v = tid; v < nvec; v += TP_THREADS) __stcg(dst + v, reinterpret_cast<const float4*>(acc)[v]);
+            }
+            __syncthreads();
+            for (int r = tid; r < 2 * vpad; r += TP_THREADS) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < TP_WARPS; w++) s += s_dot[w * 2 * vpad + r];
+                xown[r] = s;
+            }
+            const long long tB0 = clock64();
+            nbar++;
+            grid_barrier(a.barrier, nbar * (unsigned long long)G);
+
+            // ---- [B] own rows: x, z, residual, y, partial sums ------------------------------------
+            float ps[NSUM] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int rb = 0; rb < nown; rb += TP_THREADS / 8) {
+                const int r = rb + (tid >> 3), sub = tid & 7;
+                const bool act = r < nown;
+                const int i = act ? own_row(r) : 0;
+                float s = 0.f;
+                if (act) {
+#pragma unroll 4
+                    for (int c = sub; c < G; c += 8) s += __ldcg(part + (size_t)c * ld + i);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (act && sub == 0) {
+                    const float xv = __fadd_rn(xown[r < nT ? r : vpad + (r - nT)], s);
+                    const float ay = __ldcg(adj_y + i), az = __ldcg(adj_z + i), zo = __ldcg(zb(cur) + i);
+                    const float v = __fadd_rn(xv, __fdiv_rn(ay, frho));
+                    const float zn = prox_apply(v, prox);
+                    const float res = __fsub_rn(xv, zn);
+                    const float yn = __fadd_rn(ay, __fmul_rn(frho, res));
+                    zb(nxt)[i] = zn;
+                    yb(nxt)[i] = yn;
+                    const float d1 = zn - zo, d2 = zn - az;
+                    ps[0] += res * res; ps[1] += d1 * d1; ps[2] += d2 * d2;
+                    ps[3] += xv * xv;   ps[4] += zn * zn; ps[5] += yn * yn;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NSUM; q++) ps[q] = warp_sum(ps[q]);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < NSUM; q++) s_red[warp][q] = ps[q];
+            }
+            __syncthreads();
+            if (tid < NSUM) {
+                float s = 0.f;
+                for (int w = 0; w < TP_WARPS; w++) s += s_red[w][tid];
+                partials[((size_t)(git & 1u) * G + cta) * PART_STRIDE + tid] = s;
+            }
+            if (a.prof && cta == 0 && tid == 0) { const long long t = clock64(); pf[0] += (unsigned long long)(tB0 - tA0); pf[1] += (unsigned long long)(t - tB0); }
+            nbar++;
+            grid_barrier(a.barrier, nbar * (unsigned long long)G);
+            const long long tC0 = clock64();
+
+            // ---- [C] global scalars, identical in every CTA ----------------------------------------
+            if (warp < NSUM) {
+                double s = 0.0;
+                const float* src = partials + (size_t)(git & 1u) * G * PART_STRIDE + warp;
+                for (int c = lane; c < G; c += 32) s += (double)__ldcg(src + (size_t)c * PART_STRIDE);
+                s = warp_sum(s);
+                if (lane == 0) s_sum[warp] = s;
+            }
+            __syncthreads();
+            const double sum_r2 = s_sum[0], sum_dz2 = s_sum[1], sum_da2 = s_sum[2];
+            sx2 = s_sum[3]; sz2 = s_sum[4]; sy2 = s_sum[5];
+            const double resid_primal = (double)sqrtf((float)sum_r2);
+            const double resid_dual = rho * sqrt((double)(float)sum_dz2);
+            const int old = cur;
+            cur = nxt;
+
+            if (tracing && cta == 0 && tid == 0 && it < a.trace_cap) {
+                double* row = a.trace + 5 * (size_t)it;
+                row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
+                *a.trace_rows = it + 1;
+            }
+            if (a.prof && cta == 0 && tid == 0) { pf[5] += (unsigned long long)(clock64() - tC0); pf[7] += 1ULL; }
+            if (resid_primal < eps_primal && resid_dual < eps_dual) { niter = it + 1; git++; break; }
+
+            const double old_c = adj_c;
+            adj_c = rho * resid_primal * resid_primal + rho * (double)(float)sum_da2;
+            bool accel;
+            float c1 = 0.f, c2 = 0.f;
+            if (adj_c < 0.999 * old_c) {
+                const double old_a = adj_a;
+                adj_a = 0.5 + 0.5 * sqrt(1.0 + 4.0 * old_a * old_a);
+                const double ratio = (old_a - 1.0) / adj_a;
+                c1 = (float)(1.0 + ratio); c2 = (float)ratio;
+                accel = true;
+            } else {
+                adj_a = 1.0;
+                adj_c = old_c / 0.999;
+                accel = false;
+            }
+            const float* zn_ = zb(cur); const float* zo_ = zb(old);
+            const float* yn_ = yb(cur); const float* yo_ = yb(old);
+            for (int v = tid; v < nvec; v += TP_THREADS) {
+                const float4 zo = ldcg4(zo_ + 4 * v), yo = ldcg4(yo_ + 4 * v);
+                float4 az, ay;
+                if (accel) {
+                    const float4 zn = ldcg4(zn_ + 4 * v), yn = ldcg4(yn_ + 4 * v);
+                    az.x = __fsub_rn(__fmul_rn(c1, zn.x), __fmul_rn(c2, zo.x));
+                    az.y = __fsub_rn(__fmul_rn(c1, zn.y), __fmul_rn(c2, zo.y));
+                    az.z = __fsub_rn(__fmul_rn(c1, zn.z), __fmul_rn(c2, zo.z));
+                    az.w = __fsub_rn(__fmul_rn(c1, zn.w), __fmul_rn(c2, zo.w));
+                    ay.x = __fsub_rn(__fmul_rn(c1, yn.x), __fmul_rn(c2, yo.x));
+                    ay.y = __fsub_rn(__fmul_rn(c1, yn.y), __fmul_rn(c2, yo.y));
+                    ay.z = __fsub_rn(__fmul_rn(c1, yn.z), __fmul_rn(c2, yo.z));
+                    ay.w = __fsub_rn(__fmul_rn(c1, yn.w), __fmul_rn(c2, yo.w));
+                } else { az = zo; ay = yo; }
+                const float4 xy = __ldg(reinterpret_cast<const float4*>(a.XY) + v);
+                float4 o;
+                o.x = (float)((double)__fsub_rn(xy.x, ay.x) + rho * (double)az.x);
+                o.y = (float)((double)__fsub_rn(xy.y, ay.y) + rho * (double)az.y);
+                o.z = (float)((double)__fsub_rn(xy.z, ay.z) + rho * (double)az.z);
+                o.w = (float)((double)__fsub_rn(xy.w, ay.w) + rho * (double)az.w);
+                reinterpret_cast<float4*>(rhs)[v] = o;
+                const int i = 4 * v;
+                const float azv[4] = {az.x, az.y, az.z, az.w}, ayv[4] = {ay.x, ay.y, ay.z, ay.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (is_own(i + e)) { adj_z[i + e] = azv[e]; adj_y[i + e] = ayv[e]; }
+            }
+            __syncthreads();
+            if (a.prof && cta == 0 && tid == 0) pf[6] += (unsigned long long)(clock64() - tC0);
+        }
+
+        for (int r = tid; r < nown; r += TP_THREADS) {
+            const int i = own_row(r);
+            a.z_out[(size_t)k * p + i] = __ldcg(zb(cur) + i);
+        }
+        if (cta == 0 && tid == 0) a.niter_out[k] = niter;
+    }
+    if (a.prof && cta == 0 && tid == 0)
+        for (int q = 0; q < 8; q++) a.prof[q] = pf[q];
+}
+
 // stand-alone fused pass over long vectors (HBM-bound when len >> L2)
 constexpr int ZU_THREADS = 256;
 __global__ void __launch_bounds__(ZU_THREADS) fused_zu_kernel(const float* __restrict__ x, const float* __restrict__ adj_y,
@@ -485,11 +797,51 @@ size_t tall_state_floats(int p)
     return 8 * ld + 2 * (size_t)2048 * PART_STRIDE;          // partial slots: up to 8 ranks x 148 CTAs, double-buffered
 }
 
+// grid of the one-triangle kernel: folded rows per CTA and the grid size (0: the shape does not take this path)
+static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes)
+{
+    const int ld = (p + 3) & ~3;
+    const int V = (p + 1) / 2;
+    int G = std::min(sms, std::max(1, (V + 3) / 4));
+    const int vr = (V + G - 1) / G;
+    G = (V + vr - 1) / vr;
+    const int vpad = (vr + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
+    *vrows_per_cta = vr;
+    *smem_bytes = sizeof(float) * (2 * (size_t)ld + (size_t)(TP_WARPS + 1) * 2 * vpad);
+    return (*smem_bytes <= 200 * 1024) ? G : 0;
+}
+size_t tall_tri_part_floats(int p)
+{
+    int vr; size_t sm;
+    const int G = tri_grid(p, sm_count(), &vr, &sm);
+    return G > 0 ? (size_t)G * (size_t)((p + 3) & ~3) : 0;
+}
+
 int launch_tall_path(cudaStream_t s, const TallPathArgs& a)
 {
     const int p = a.p;
     const int ld = (p + 3) & ~3;
     const int sms = sm_count();
+    if (a.tri_part != nullptr && a.nranks <= 1) {
+        int vr; size_t smem;
+        const int G = tri_grid(p, sms, &vr, &smem);
+        if (G > 0) {
+            static size_t tri_smem_set = 0;
+            if (smem > tri_smem_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(tall_path_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                tri_smem_set = smem;
+            }
+            int occ = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tall_path_tri_kernel, TP_THREADS, smem));
+            if (occ < 1) throw CudaError("tall path (triangle) kernel does not fit on an SM");
+            TallPathArgs args = a;
+            int vri = vr, ldi = ld;
+            void* params[] = { (void*)&args, (void*)&vri, (void*)&ldi };
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tall_path_tri_kernel, dim3(G), dim3(TP_THREADS), params, smem, s));
+            ++g_launch_count;
+            return G;
+        }
+    }
     // enough rows per CTA to amortise the barrier; never more CTAs than SMs (co-residency)
     // rows of this rank (the kernel uses the same split); every rank must run the SAME G for the partial slots
     const int NR = a.nranks > 1 ? a.nranks : 1;

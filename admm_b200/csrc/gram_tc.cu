@@ -1168,12 +1168,13 @@ gram_pair_h_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
 
     if (warp == 0) {
         // ================================ TMA producer (each CTA) =======================
-        // Lock step (slice-major full rounds only): the 74 CTA pairs of a round share ~35 operand panels, but the reuse
-        // only happens in the 126 MB L2 if the pairs read the same rows at about the same time (ncu, profiles/r1s: 1.18 TB
-        // of DRAM reads for a 40 GB operand array, L2 hit rate 36 %, a third of the power budget).  Every H_SYNC stages
-        // the leader publishes the pair's stage count and both producers hold back while they are more than `lead` stages
+        // Optional lock step (lead > 0, slice-major full rounds only): the 74 CTA pairs of a round share ~35 operand
+        // panels, but the reuse only happens in the 126 MB L2 if the pairs read the same rows at about the same time
+        // (ncu, profiles/r2i: 1.11 TB of DRAM reads for a 40 GB operand array, L2 hit rate 37 %).  Every H_SYNC stages the
+        // leader publishes the pair's stage count and both producers hold back while they are more than `lead` stages
         // ahead of the slowest pair.  The wait is bounded: a pair that cannot see progress (a CTA pair not resident, e.g.
-        // under MPS) stops throttling for the rest of the launch instead of hanging.
+        // under MPS) stops throttling for the rest of the launch instead of hanging.  See the launch site for why it is
+        // off by default.
         Ring r;
         HItem it;
         int gstage = 0;
@@ -1553,13 +1554,17 @@ bool gram_tn_f16_blocked(cudaStream_t s, const void* Xb, i64 n, i64 p, float* G,
         // tile-major, SM clock under the power cap 997 against 930 MHz; results bit-identical); "tile" reverts
         const char* oenv = getenv("B200ADMM_GRAM_ORDER");
         const int slice_major = (oenv && !strcmp(oenv, "tile")) ? 0 : 1;
-        // lock step of the pairs' producers (see the kernel): lead in stages, B200ADMM_GRAM_LEAD=0 switches it off
+        // lock step of the pairs' producers (see the kernel): B200ADMM_GRAM_LEAD = lead in stages.  OFF by default:
+        // measured (profiles/r2j_gram_lockstep_sweep.txt) it cuts the DRAM reads of a launch from 1107 GB to 337 GB
+        // (L2 hit rate 37 % -> 65 %) and the SM clock under the 1000 W cap rises from 1.27 to 1.57 GHz, but the tensor
+        // pipe then waits for the slowest pair (88 % -> 69 % busy) and the kernel is 2-6 % slower: what the cap limits
+        // is the energy of the MMAs themselves, not DRAM power.
         static int* prog = nullptr;
         if (!prog) CUDA_CHECK(cudaMalloc(&prog, sizeof(int) * 256));
         static int lead = -1;
         if (lead < 0) {
             const char* lenv = getenv("B200ADMM_GRAM_LEAD");
-            lead = lenv ? atoi(lenv) : 32;
+            lead = lenv ? atoi(lenv) : 0;
         }
         if (slice_major && lead > 0) CUDA_CHECK(cudaMemsetAsync(prog, 0, sizeof(int) * 256, s));
         gram_pair_h_kernel<<<2 * npairs, H_THREADS, H_SMEM, s>>>(map, G, (int)p, (long long)ld, (int)nk, I0, ntiles, scratch, counters, slice_major,

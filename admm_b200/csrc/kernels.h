@@ -139,8 +139,12 @@ struct TallPathArgs {
     size_t off_zout = 0;    // float offset of z_out inside a block
     int* abort_flag = nullptr;   // device int (local), zeroed; set when a peer did not arrive in time
     unsigned long long* prof = nullptr;   // optional (B200ADMM_PATH_PROF=1): 8 cycle counters of CTA 0, summed over the path
+    // single GPU: workspace of tall_tri_part_floats(p) floats selects the kernel that reads one triangle of Kinv per
+    // iteration (nullptr: the full-row kernel)
+    float* tri_part = nullptr;
 };
 size_t tall_state_floats(int p);
+size_t tall_tri_part_floats(int p);   // 0: p too large for the one-triangle kernel
 // returns the grid size used
 int launch_tall_path(cudaStream_t s, const TallPathArgs& a);
 

@@ -472,6 +472,13 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     if (getenv("B200ADMM_PATH_PROF")) { prof_dev.alloc(8); prof_dev.zero(s); a.prof = prof_dev.p; }
     const char* snake_env = getenv("B200ADMM_SNAKE");
     a.snake = snake_env ? atoi(snake_env) : 1;
+    // one GPU: read one triangle of the symmetric K^-1 per iteration (B200ADMM_TALL_TRI=0: the full-row kernel)
+    DevBuf<float> tri_part;
+    const char* tri_env = getenv("B200ADMM_TALL_TRI");
+    if (!pb && !(tri_env && !strcmp(tri_env, "0"))) {
+        const size_t nf = tall_tri_part_floats((int)p);
+        if (nf) { tri_part.alloc(nf); a.tri_part = tri_part.p; }
+    }
     tm.start();
     launch_tall_path(s, a);
     T.iterate = tm.stop();

@@ -201,6 +201,34 @@ def tall_bytes_per_iter(p):
     return 4.0 * p * (p + 1) + 64.0 * p
 
 
+def tri_kernel_in_use(world):
+    """One GPU (and B200ADMM_TALL_TRI not 0): the iteration kernel reads one triangle of the symmetric K^-1."""
+    return world == 1 and os.environ.get("B200ADMM_TALL_TRI", "1") != "0"
+
+
+def iteration_roofline(env, p, niter_path, iterate_s, world, tr_iter):
+    """The per-iteration hot path named by BASELINE.json: one persistent launch for the whole lambda path.  Two byte
+    counts per iteration: SURVEY.md section 8(d)'s 4 p (p + 1) + 64 p (the reference's two triangular solves = one full
+    read of K^-1) and 2 p (p + 1) + 64 p (one triangle of the symmetric K^-1).  `frac` is quoted on the bytes the
+    kernel in use has to read: the triangle on one GPU (tall_path_tri_kernel), the full rows on row-sharded runs."""
+    full = tall_bytes_per_iter(p)
+    tri = 2.0 * p * (p + 1) + 64.0 * p
+    use_tri = tri_kernel_in_use(world)
+    ach_full = full * niter_path / iterate_s / 1e9
+    ach_tri = tri * niter_path / iterate_s / 1e9
+    ach = ach_tri if use_tri else ach_full
+    return {"kernel": ("tall_path_tri_kernel (persistent lambda-path iteration kernel, one triangle of K^-1 per iteration)" if use_tri
+                       else "tall_path_kernel (persistent lambda-path iteration kernel, full rows of K^-1)"),
+            "bound": "hbm", "achieved": ach, "peak": env.hbm_peak, "unit": "GB/s", "frac": ach / env.hbm_peak,
+            "bytes_per_iteration": tri if use_tri else full,
+            "achieved_on_reference_bytes": ach_full, "frac_on_reference_bytes": ach_full / env.hbm_peak, "reference_bytes_per_iteration": full,
+            "achieved_one_triangle": ach_tri,
+            "traffic": (tr_iter["dram_bytes_per_iteration"] * niter_path if tr_iter else None),
+            "traffic_source": (tr_iter["source"] if tr_iter else None),
+            "traffic_unit": "bytes per launch (one launch = the whole lambda path)", "peak_source": env.peak_src,
+            "us_per_iteration": iterate_s / max(niter_path, 1) * 1e6}
+
+
 def ref_fit_file(args):
     return os.path.join(tempfile.gettempdir(), "b200admm_ref_%s_n%d_p%d_l%d_s%d.npz" % (args.config, args.n, args.p, args.nlambda, args.seed))
 
@@ -509,7 +537,7 @@ def run_tall(args, enet=False):
     nb = (p + 255) // 256
     gram_exec_tflops = 3.0 * 2.0 * n_local * 65536.0 * (nb * (nb + 1) // 2) / max(gram_kernel_s, 1e-9) / 1e12
     tr_gram = ncu_traffic("gram_pair_h_kernel", n_local, p)
-    tr_iter = ncu_traffic("tall_path_kernel", n, p)
+    tr_iter = ncu_traffic("tall_path_tri_kernel" if tri_kernel_in_use(world) else "tall_path_kernel", n, p)
     name = ("enet_tall_n%d_p%d_alpha0.5_1lambda" if enet else "lasso_tall_n%d_p%d_" + "%dlambda" % nl) % (n, p)
     line = env.base_line("admm_iters_per_sec_full_lambda_path", UNIT, total_iters / dev_s, dev_s, "strong", "f32", {
         "workload": name, "n": n, "p": p, "nlambda": nl, "standardize": True, "intercept": True, "eps_abs": 1e-5, "eps_rel": 1e-5,
@@ -530,13 +558,7 @@ def run_tall(args, enet=False):
         # the per-iteration hot path named by BASELINE.json: one persistent launch for the whole lambda path.  Two
         # byte counts: SURVEY.md section 8(d)'s 4 p (p + 1) + 64 p (the reference's two triangular solves = what a full
         # K^-1 read costs) and the symmetric minimum 2 p (p + 1) + 64 p (one triangle of K^-1).
-        "roofline_iteration": {"kernel": "tall_path_kernel (persistent lambda-path iteration kernel)", "bound": "hbm",
-                               "achieved": achieved, "peak": env.hbm_peak, "unit": "GB/s", "frac": achieved / env.hbm_peak,
-                               "achieved_one_triangle": (2.0 * p * (p + 1) + 64.0 * p) * niter_path / T["iterate"] / 1e9,
-                               "traffic": (tr_iter["dram_bytes_per_iteration"] * niter_path if tr_iter else None),
-                               "traffic_source": (tr_iter["source"] if tr_iter else None),
-                               "traffic_unit": "bytes per launch (one launch = the whole lambda path)", "peak_source": env.peak_src,
-                               "bytes_per_iteration": bpi, "us_per_iteration": T["iterate"] / max(niter_path, 1) * 1e6},
+        "roofline_iteration": iteration_roofline(env, p, niter_path, T["iterate"], world, tr_iter),
         "setup_flops": {"gram_syrk_flop": gram_flops, "gram_phase_tflops": gram_flops / world / max(T["gram"], 1e-9) / 1e12,
                         "factor_flop": float(p) ** 3, "factor_tflops": float(p) ** 3 / max(T["factor"], 1e-9) / 1e12},
         "clocks": clocks, "gpu_launches": int(launches), "device": env.info["name"]})

@@ -111,6 +111,33 @@ def test_exhausted_lambda_then_warm_start_is_deterministic(A, O):
             assert np.array_equal(b, ref)
 
 
+@pytest.mark.parametrize("n,p", [(4000, 37), (6000, 1001), (9000, 2310), (5000, 4100)])
+def test_one_triangle_and_full_row_iteration_kernels_agree(A, O, monkeypatch, n, p):
+    """The single-GPU path kernel reads one triangle of the symmetric K^-1 (tall_path_tri_kernel); the row-sharded runs
+    and B200ADMM_TALL_TRI=0 read the full rows (tall_path_kernel).  Same algorithm, different summation order of the
+    K^-1 product: both against the oracle, against each other per iteration over the first iterations (trace), and the
+    triangle kernel bit-identical over repeated runs.  Sizes: odd p (a middle row), p not a multiple of 4, folded row
+    blocks with a ragged last CTA, several 2048-column stripes."""
+    from admm_b200 import _capi as K
+    x, y = gaussian_problem(n, p, seed=n + p, nsig=min(20, p // 2))
+    o = O.lasso_path(x, y, nlambda=12)
+    fits, traces = {}, {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200ADMM_TALL_TRI", mode)
+        with K.trace(which=0, cap=60) as tr:
+            fits[mode] = A.admm_lasso(x, y).penalty(nlambda=12).fit()
+        traces[mode] = tr.rows.copy()
+    report("tall n=%d p=%d one-triangle kernel" % (n, p), dense(fits["1"].beta), o["beta"], fits["1"].niter, o["niter"], 2e-4, 2e-4)
+    report("tall n=%d p=%d full-row kernel" % (n, p), dense(fits["0"].beta), o["beta"], fits["0"].niter, o["niter"], 2e-4, 2e-4)
+    m = min(len(traces["1"]), len(traces["0"]), 10)
+    assert m >= 3
+    assert np.allclose(traces["1"][:m], traces["0"][:m], rtol=1e-3, atol=1e-12)
+    assert np.abs(fits["1"].niter.astype(int) - fits["0"].niter.astype(int)).max() <= 3
+    monkeypatch.setenv("B200ADMM_TALL_TRI", "1")
+    again = A.admm_lasso(x, y).penalty(nlambda=12).fit()
+    assert np.array_equal(dense(again.beta), dense(fits["1"].beta)) and np.array_equal(again.niter, fits["1"].niter)
+
+
 def test_single_default_lambda_is_the_low_end(A, O):
     x, y = gaussian_problem(3000, 40, seed=4, nsig=5)
     f = A.admm_lasso(x, y).penalty(nlambda=1).fit()
