@@ -42,6 +42,10 @@ struct StdStats {
 };
 void standardize_all(cudaStream_t s, const float* X_in, i64 ld_in, float* X_out, i64 ld_out, float* y, i64 n_local, i64 n_total, i64 p,
                      int flag, float* d_meanX, float* d_scaleX, StdStats& st);
+void standardize_y_sharded(cudaStream_t s, float* y, i64 n_local, i64 n_total, int flag, StdStats& st);
+void standardize_stats3_sharded(cudaStream_t s, const float* X_in, i64 ld_in, i64 n_local, i64 n_total, i64 pc,
+                                float* d_meanX, float* d_scaleX, float* d_inv, float* tmp);
+void fetch_std_stats(cudaStream_t s, i64 p, int flag, const float* d_meanX, const float* d_scaleX, StdStats& st);
 
 namespace {
 
@@ -147,12 +151,20 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
     memset(&T, 0, sizeof T);
 
     // ---- ingest + global DataStd (ParLasso.cpp:45-69: standardisation happens before the split) ----
+    // One block per rank on device-resident float32 data with both DataStd flags (the multi-GPU deployment): the raw
+    // columns are read in place -- statistics, then ONE pass that standardises, forms A'b and writes the fp16 operands
+    // of the Gram kernel (gram_std_split_xty, as on the tall path); no standardised float32 copy exists (40 GB per rank
+    // at n = 1e6 x p = 8e4 over eight GPUs).
+    const char* gram_env = getenv("B200ADMM_GRAM");
+    const bool fused_block = cm.active() && d->dtype == B200ADMM_F32_DEVICE && flag == 3 && n_local >= p && !gram_env &&
+                             (double)n < 4.0e9 && gram_f16_usable(n_local, p);
     const i64 ldx = (n_local + 3) & ~(i64)3;
-    DevBuf<float> Xs((size_t)ldx * (size_t)p), ys(n_local), Xtmp;
+    DevBuf<float> Xs, ys(n_local), Xtmp;
+    if (!fused_block) Xs.alloc((size_t)ldx * (size_t)p);
     const float* X_in = Xs.p;
     i64 ld_in = ldx;
     tm.start();
-    if (ldx != n_local) Xs.zero(s);
+    if (!fused_block && ldx != n_local) Xs.zero(s);
     if (d->dtype == B200ADMM_F32_DEVICE) {
         X_in = (const float*)d->x; ld_in = n_local;
         CUDA_CHECK(cudaMemcpyAsync(ys.p, d->y, n_local * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -163,10 +175,18 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
         ingest_f32(s, d->y, d->dtype, (size_t)n_local, ys.p);
     }
     T.ingest = tm.stop();
-    DevBuf<float> d_meanX(p), d_scaleX(p);
+    DevBuf<float> d_meanX(p), d_scaleX(p), d_inv;
     StdStats st;
     tm.start();
-    standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    if (fused_block) {
+        DevBuf<float> tmp(2 * p + 8);
+        d_inv.alloc(p);
+        standardize_y_sharded(s, ys.p, n_local, n, flag, st);
+        standardize_stats3_sharded(s, X_in, ld_in, n_local, n, p, d_meanX.p, d_scaleX.p, d_inv.p, tmp.p);
+        fetch_std_stats(s, p, flag, d_meanX.p, d_scaleX.p, st);
+    } else {
+        standardize_all(s, X_in, ld_in, Xs.p, ldx, ys.p, n_local, n, p, flag, d_meanX.p, d_scaleX.p, st);
+    }
     T.standardize = tm.stop();
     Xtmp.release();
 
@@ -191,14 +211,23 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
 
     // ---- A_i'b_i, lambda0 = max |X'y| ---------------------------------------------------------------
     DevBuf<float> xy(p);
+    DevBuf<unsigned char> Xb;
     tm.start();
     for (size_t i = 0; i < blocks.size(); i++) {
         Block& b = *blocks[i];
         b.tall = b.rows >= p;
         b.Ab.alloc(p); b.x.alloc(p); b.y.alloc(p);
-        gemv_t<float>(s, Xs.p + b.row0, b.rows, p, ldx, ys.p + b.row0, b.Ab.p);
+        if (!fused_block) gemv_t<float>(s, Xs.p + b.row0, b.rows, p, ldx, ys.p + b.row0, b.Ab.p);
     }
-    gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, xy.p);       // X'y over all local rows, as the master does
+    if (fused_block) {
+        Block& b = *blocks[0];
+        Xb.alloc(gram_f16_blocked_bytes(n_local, p));
+        DevBuf<float> xty_work(gram_f16_xty_work_floats(n_local, p));
+        gram_std_split_xty(s, X_in, n_local, ld_in, p, 0, p, d_meanX.p, d_inv.p, ys.p, Xb.p, b.Ab.p, xty_work.p);
+        CUDA_CHECK(cudaMemcpyAsync(xy.p, b.Ab.p, p * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else {
+        gemv_t<float>(s, Xs.p, n_local, p, ldx, ys.p, xy.p);   // X'y over all local rows, as the master does
+    }
     allreduce_sum(s, xy.p, p);
     std::vector<float> h_xy(p);
     CUDA_CHECK(cudaMemcpyAsync(h_xy.data(), xy.p, p * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -221,12 +250,19 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
     const float frho = (float)rho;
 
     // ---- per block: Gram + rho I, explicit inverse (PADMMLasso_Worker::init) --------------------------
-    const char* gram_env = getenv("B200ADMM_GRAM");
     const bool want_tensor = !(gram_env && !strcmp(gram_env, "simt"));
+    // (all Gram matrices first, then -- once the standardised copy is no longer needed -- the inverses: at p = 8e4 the
+    // copy is 40 GB per rank and the factorisation needs three more p x p arrays next to K_i^-1)
     for (size_t i = 0; i < blocks.size(); i++) {
         Block& b = *blocks[i];
         const float* A = Xs.p + b.row0;
-        if (b.tall) {
+        if (b.tall && fused_block) {
+            b.Kinv.alloc((size_t)p * (size_t)ld);
+            b.Kinv.zero(s);
+            if (!gram_tn_f16_blocked(s, Xb.p, n_local, p, b.Kinv.p, ld)) throw CudaError("fp16 Gram kernel declined the shape");
+            if (gram_f16_overflowed(s)) throw CudaError("fp16 Gram split: a standardised value exceeds sqrt(n)");
+            add_to_diagonal(s, b.Kinv.p, ld, p, frho);
+        } else if (b.tall) {
             b.Kinv.alloc((size_t)p * (size_t)ld);
             b.Kinv.zero(s);
             // (the tensor kernel declines block starts that are not 16-byte aligned; CUDA cores then)
@@ -238,25 +274,26 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
             if (!on_tensor)
                 gemm<float>(s, true, false, p, p, b.rows, 1.f, A, ldx, A, ldx, 0.f, b.Kinv.p, ld, GEMM_LOWER | GEMM_MIRROR);
             add_to_diagonal(s, b.Kinv.p, ld, p, frho);
-            DevBuf<float> W((size_t)p * (size_t)ld);
-            int info = 0;
-            spd_inverse<float>(s, b.Kinv.p, p, ld, W.p, &info, nullptr);
         } else {
             const i64 m = b.rows;
             b.Kinv.alloc((size_t)m * (size_t)m);
             gemm<float>(s, false, true, m, m, p, 1.f, A, ldx, A, ldx, 0.f, b.Kinv.p, m, GEMM_LOWER | GEMM_MIRROR);
             add_to_diagonal(s, b.Kinv.p, m, m, frho);
-            DevBuf<float> W((size_t)m * (size_t)m);
-            int info = 0;
-            spd_inverse<float>(s, b.Kinv.p, m, m, W.p, &info, nullptr);
             b.t1.alloc(m); b.t2.alloc(std::max<i64>(m, p)); b.work.alloc(gemv_n_work(m, p));
         }
         b.x.zero(s); b.y.zero(s);
     }
-    T.gram = tm.stop();          // Gram and factorisation are interleaved per block; reported together
     bool keep_X = false;
     for (auto& b : blocks) if (!b->tall) keep_X = true;
-    if (!keep_X) { Xs.release(); ys.release(); }
+    if (!keep_X) { CUDA_CHECK(cudaStreamSynchronize(s)); Xs.release(); Xb.release(); ys.release(); }
+    for (size_t i = 0; i < blocks.size(); i++) {
+        Block& b = *blocks[i];
+        const i64 m = b.tall ? p : b.rows, ldk = b.tall ? ld : b.rows;
+        DevBuf<float> W((size_t)m * (size_t)ldk);
+        int info = 0;
+        spd_inverse<float>(s, b.Kinv.p, m, ldk, W.p, &info, nullptr);
+    }
+    T.gram = tm.stop();          // Gram and factorisation of all blocks; reported together
 
     // ---- iterations ------------------------------------------------------------------------------------
     DevBuf<float> z(p), rhs(p), payload(p + 3), zout2(2), local_tail(2);

@@ -431,36 +431,47 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
 // the K^-1 product differs.  Needs 2 p floats of shared memory (rhs + column sums): p <= ~25 000; row-sharded runs keep
 // tall_path_kernel (their exchange is per row block).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TRI_ROWS = 8;                 // rows per group (loads in flight per thread)
-constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe
+constexpr int TRI_ROWS = 4;                 // rows per step
+constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe (one float4 per thread)
+constexpr int TRI_STEP_BYTES = TRI_ROWS * TP_THREADS * 16;   // 32 KB of K^-1 per step and CTA
 
-// v[0..7] per lane -> the lanes with (lane & 3) == 0 return the warp total of row ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
-__device__ __forceinline__ float butterfly8(float (&v)[TRI_ROWS], int lane)
+// 16-byte global -> shared copy that bypasses the register file (src_bytes = 0: the slot is zero-filled, nothing is read)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int nbytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// v[0..3] per lane -> the lanes with (lane & 7) == 0 return the warp total of row ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)
+__device__ __forceinline__ float butterfly4(float (&v)[TRI_ROWS], int lane)
 {
     const unsigned full = 0xffffffffu;
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float send = h16 ? v[k] : v[k + 4];
-        const float keep = h16 ? v[k + 4] : v[k];
-        v[k] = keep + __shfl_xor_sync(full, send, 16);
-    }
+    const bool h16 = lane & 16, h8 = lane & 8;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const float send = h8 ? v[k] : v[k + 2];
-        const float keep = h8 ? v[k + 2] : v[k];
-        v[k] = keep + __shfl_xor_sync(full, send, 8);
+        const float send = h16 ? v[k] : v[k + 2];
+        const float keep = h16 ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(full, send, 16);
     }
     {
-        const float send = h4 ? v[0] : v[1];
-        const float keep = h4 ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(full, send, 4);
+        const float send = h8 ? v[0] : v[1];
+        const float keep = h8 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 8);
     }
+    v[0] += __shfl_xor_sync(full, v[0], 4);
     v[0] += __shfl_xor_sync(full, v[0], 2);
     v[0] += __shfl_xor_sync(full, v[0], 1);
     return v[0];
 }
 
+// NST = steps of K^-1 in flight per CTA (cp.async ring in shared memory, NST x 32 KB): the sweep is a chain of
+// ~60 steps per iteration and a step that waits for its own loads is latency-bound (measured with register loads:
+// 4.6 TB/s, 35 % of the DRAM rate busy); with the ring the loads of the next NST - 1 steps are always under way.
+// Every thread copies and later reads ONLY its own 16-byte slots, so the ring needs no barrier, just wait_group.
+template <int NST>
 __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathArgs a, int vrows_per_cta, int ld)
 {
     extern __shared__ __align__(16) float smem[];
@@ -469,6 +480,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
     float* s_dot = acc + ld;                             // [TP_WARPS][2 * vpad]: per-warp row sums
     const int vpad = (vrows_per_cta + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
     float* xown = s_dot + TP_WARPS * 2 * vpad;           // [2 * vpad]: row sums of the own rows
+    float4* ring = reinterpret_cast<float4*>(xown + 2 * vpad);   // [NST][TRI_ROWS][TP_THREADS]
     __shared__ double s_sum[NSUM];
     __shared__ float s_red[TP_WARPS][NSUM];
 
@@ -500,6 +512,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
     unsigned long long nbar = 0;
     unsigned git = 0;
     unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS, ng = ngT + ngB;
 
     for (int k = 0; k < a.nl; k++) {
         const float lambda = (float)a.lambdas[k];
@@ -529,26 +542,56 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
             // ---- [A] lower-triangle sweep of the own rows --------------------------------------------
             for (int v = tid; v < nvec; v += TP_THREADS) reinterpret_cast<float4*>(acc)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool rev = a.snake && (git & 1u);
-            const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS;
-            for (int gg = 0; gg < ngT + ngB; gg++) {
-                const int g = rev ? (ngT + ngB - 1 - gg) : gg;
+            // group gg of the sweep (4 rows of one block): first row, rows, slot of its row sums
+            auto group = [&](int gg, int& i0, int& nr, int& slot) {
+                const int g = rev ? (ng - 1 - gg) : gg;
                 const bool bottom = g >= ngT;
-                const int g0 = (bottom ? g - ngT : g) * TRI_ROWS;              // first row of the group within its block
-                const int blk0 = bottom ? b0 : t0, blkn = bottom ? nB : nT;
-                const int i0 = blk0 + g0;                                      // smallest row of the group
-                const int nr = min(TRI_ROWS, blkn - g0);
+                const int g0 = (bottom ? g - ngT : g) * TRI_ROWS;
+                i0 = (bottom ? b0 : t0) + g0;
+                nr = min(TRI_ROWS, (bottom ? nB : nT) - g0);
+                slot = (bottom ? vpad : 0) + g0;
+            };
+            // producer cursor: (group, stripe) of the next step to put in flight
+            int pg = 0, pst = 0, pi0 = 0, pnr = 0, pslot = 0, pstage = 0;
+            if (ng > 0) group(0, pi0, pnr, pslot);
+            auto issue = [&]() {
+                if (pg < ng) {
+                    const int c4 = pst * TP_THREADS + tid, j0 = 4 * c4;
+                    float4* dst = ring + (size_t)pstage * TRI_ROWS * TP_THREADS + tid;
+#pragma unroll
+                    for (int r = 0; r < TRI_ROWS; r++) {
+                        const bool valid = r < pnr && j0 <= pi0 + r;
+                        cp_async16(dst + r * TP_THREADS, valid ? (a.Kinv + (size_t)(pi0 + r) * ld + j0) : a.Kinv, valid);
+                    }
+                    pst++;
+                    if (pst * TRI_STRIPE > pi0 + pnr - 1) {          // stripe starts beyond the group's longest row
+                        pst = 0; pg++;
+                        if (pg < ng) group(pg, pi0, pnr, pslot);
+                    }
+                }
+                cp_async_commit();                                    // (an empty group once the sweep is exhausted)
+                pstage = pstage + 1 == NST ? 0 : pstage + 1;
+            };
+#pragma unroll
+            for (int q = 0; q < NST - 1; q++) issue();
+            int cstage = 0;
+            for (int gg = 0; gg < ng; gg++) {
+                int i0, nr, slot;
+                group(gg, i0, nr, slot);
                 const int imax = i0 + nr - 1;
                 float d[TRI_ROWS], ri[TRI_ROWS];
 #pragma unroll
                 for (int r = 0; r < TRI_ROWS; r++) { d[r] = 0.f; ri[r] = r < nr ? rhs[i0 + r] : 0.f; }
-                const float* kbase = a.Kinv + (size_t)i0 * ld;
-                for (int c4 = tid; 4 * c4 <= imax; c4 += TP_THREADS) {
-                    const int j0 = 4 * c4;
+                for (int st = 0; st * TRI_STRIPE <= imax; st++) {
+                    issue();
+                    cp_async_wait<NST - 1>();
+                    const int c4 = st * TP_THREADS + tid, j0 = 4 * c4;
+                    const float4* src = ring + (size_t)cstage * TRI_ROWS * TP_THREADS + tid;
+                    cstage = cstage + 1 == NST ? 0 : cstage + 1;
+                    if (j0 > imax) continue;                           // (slots were zero-filled; nothing to add)
                     float4 q[TRI_ROWS];
 #pragma unroll
-                    for (int r = 0; r < TRI_ROWS; r++)
-                        q[r] = (r < nr && j0 <= i0 + r) ? ld_stream_f4(reinterpret_cast<const float4*>(kbase + (size_t)r * ld) + c4)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < TRI_ROWS; r++) q[r] = src[r * TP_THREADS];
                     const float4 rj = reinterpret_cast<const float4*>(rhs)[c4];
                     float4 av = reinterpret_cast<float4*>(acc)[c4];
                     if (j0 + 3 < i0) {
@@ -563,7 +606,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
                     } else {
 #pragma unroll
                         for (int r = 0; r < TRI_ROWS; r++) {
-                            const int i = i0 + r;                              // rows beyond nr were loaded as zeros
+                            const int i = i0 + r;                              // rows beyond nr arrive as zeros
                             const float qx = j0 <= i ? q[r].x : 0.f, qy = j0 + 1 <= i ? q[r].y : 0.f;
                             const float qz = j0 + 2 <= i ? q[r].z : 0.f, qw = j0 + 3 <= i ? q[r].w : 0.f;
                             d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
@@ -574,12 +617,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
                     }
                     reinterpret_cast<float4*>(acc)[c4] = av;
                 }
-                const float tot = butterfly8(d, lane);
-                if ((lane & 3) == 0) {
-                    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    s_dot[warp * 2 * vpad + (bottom ? vpad : 0) + g0 + r] = tot;
-                }
+                const float tot = butterfly4(d, lane);
+                if ((lane & 7) == 0) s_dot[warp * 2 * vpad + slot + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
             }
+            cp_async_wait<0>();
             // the CTA's partial column sums -> global (every thread stores the slots it owns)
             {
                 float4* dst = reinterpret_cast<float4*>(part + (size_t)cta * ld);
@@ -604,8 +645,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
                 const int i = act ? own_row(r) : 0;
                 float s = 0.f;
                 if (act) {
-#pragma unroll 4
-                    for (int c = sub; c < G; c += 8) s += __ldcg(part + (size_t)c * ld + i);
+                    // all loads first (G <= 148 -> at most 19 per thread), then the sum in CTA order
+                    float pv[19];
+#pragma unroll
+                    for (int q = 0; q < 19; q++) { const int c = sub + 8 * q; pv[q] = c < G ? __ldcg(part + (size_t)c * ld + i) : 0.f; }
+#pragma unroll
+                    for (int q = 0; q < 19; q++) s += pv[q];
+                    for (int c = sub + 8 * 19; c < G; c += 8) s += __ldcg(part + (size_t)c * ld + i);
                 }
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -797,8 +843,8 @@ size_t tall_state_floats(int p)
     return 8 * ld + 2 * (size_t)2048 * PART_STRIDE;          // partial slots: up to 8 ranks x 148 CTAs, double-buffered
 }
 
-// grid of the one-triangle kernel: folded rows per CTA and the grid size (0: the shape does not take this path)
-static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes)
+// grid of the one-triangle kernel: folded rows per CTA, ring depth and the grid size (0: the shape does not take this path)
+static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes, int* nst)
 {
     const int ld = (p + 3) & ~3;
     const int V = (p + 1) / 2;
@@ -807,13 +853,16 @@ static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes)
     G = (V + vr - 1) / vr;
     const int vpad = (vr + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
     *vrows_per_cta = vr;
-    *smem_bytes = sizeof(float) * (2 * (size_t)ld + (size_t)(TP_WARPS + 1) * 2 * vpad);
-    return (*smem_bytes <= 200 * 1024) ? G : 0;
+    const size_t fixed = sizeof(float) * (2 * (size_t)ld + (size_t)(TP_WARPS + 1) * 2 * vpad);
+    const size_t budget = 225 * 1024;
+    *nst = fixed + 4 * (size_t)TRI_STEP_BYTES <= budget ? 4 : (fixed + 2 * (size_t)TRI_STEP_BYTES <= budget ? 2 : 0);
+    *smem_bytes = fixed + (size_t)*nst * TRI_STEP_BYTES;
+    return *nst ? G : 0;
 }
 size_t tall_tri_part_floats(int p)
 {
-    int vr; size_t sm;
-    const int G = tri_grid(p, sm_count(), &vr, &sm);
+    int vr, nst; size_t sm;
+    const int G = tri_grid(p, sm_count(), &vr, &sm, &nst);
     return G > 0 ? (size_t)G * (size_t)((p + 3) & ~3) : 0;
 }
 
@@ -823,21 +872,23 @@ int launch_tall_path(cudaStream_t s, const TallPathArgs& a)
     const int ld = (p + 3) & ~3;
     const int sms = sm_count();
     if (a.tri_part != nullptr && a.nranks <= 1) {
-        int vr; size_t smem;
-        const int G = tri_grid(p, sms, &vr, &smem);
+        int vr, nst; size_t smem;
+        const int G = tri_grid(p, sms, &vr, &smem, &nst);
         if (G > 0) {
-            static size_t tri_smem_set = 0;
-            if (smem > tri_smem_set) {
-                CUDA_CHECK(cudaFuncSetAttribute(tall_path_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                tri_smem_set = smem;
+            const void* fn = nst == 4 ? (const void*)tall_path_tri_kernel<4> : (const void*)tall_path_tri_kernel<2>;
+            static size_t tri_smem_set[2] = {0, 0};
+            size_t& set = tri_smem_set[nst == 4 ? 1 : 0];
+            if (smem > set) {
+                CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                set = smem;
             }
             int occ = 0;
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tall_path_tri_kernel, TP_THREADS, smem));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TP_THREADS, smem));
             if (occ < 1) throw CudaError("tall path (triangle) kernel does not fit on an SM");
             TallPathArgs args = a;
             int vri = vr, ldi = ld;
             void* params[] = { (void*)&args, (void*)&vri, (void*)&ldi };
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tall_path_tri_kernel, dim3(G), dim3(TP_THREADS), params, smem, s));
+            CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(TP_THREADS), params, smem, s));
             ++g_launch_count;
             return G;
         }

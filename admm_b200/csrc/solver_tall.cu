@@ -29,7 +29,7 @@ struct StdStats {
 };
 
 // y in place; returns meanY / scaleY on the host (one small synchronising read)
-static void standardize_y_sharded(cudaStream_t s, float* y, i64 n_local, i64 n_total, int flag, StdStats& st)
+void standardize_y_sharded(cudaStream_t s, float* y, i64 n_local, i64 n_total, int flag, StdStats& st)
 {
     if (flag == 0) return;
     DevBuf<float> tmp(4);
@@ -93,7 +93,7 @@ static void standardize_cols_sharded(cudaStream_t s, const float* X_in, i64 ld_i
 
 // DataStd flag 3 statistics of a column panel without the apply step (the fp16 Gram path applies them while
 // it splits the operands): meanX, scaleX and inv = 1 / scaleX, exactly as in standardize_cols_sharded case 3.
-static void standardize_stats3_sharded(cudaStream_t s, const float* X_in, i64 ld_in, i64 n_local, i64 n_total, i64 pc,
+void standardize_stats3_sharded(cudaStream_t s, const float* X_in, i64 ld_in, i64 n_local, i64 n_total, i64 pc,
                                        float* d_meanX, float* d_scaleX, float* d_inv, float* tmp)
 {
     float* sums = tmp;
@@ -105,7 +105,7 @@ static void standardize_stats3_sharded(cudaStream_t s, const float* X_in, i64 ld
     scale_from_sumsq<float>(s, d_scaleX, pc, n_total, false, d_scaleX, d_inv);
 }
 
-static void fetch_std_stats(cudaStream_t s, i64 p, int flag, const float* d_meanX, const float* d_scaleX, StdStats& st)
+void fetch_std_stats(cudaStream_t s, i64 p, int flag, const float* d_meanX, const float* d_scaleX, StdStats& st)
 {
     st.meanX.assign(p, 0.f);
     st.scaleX.assign(p, 1.f);

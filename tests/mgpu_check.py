@@ -49,7 +49,27 @@ def main():
     x2s, y2s = np.asfortranarray(x2[q0:q0 + qn]), y2[q0:q0 + qn].copy()
     ref2 = admm_b200.admm_lasso(x2, y2).penalty(nlambda=8).fit()
 
+    # consensus on device-resident float32 row blocks with p >= 256: the fused DataStd + A'b + fp16-operand pass
+    # (no standardised copy) that BASELINE config 5 runs at n = 1e6 x p = 8e4
+    n3, p3 = 900 * world + 37, 320
+    x3 = np.asfortranarray(rng.normal(0.1, 2.0, size=(n3, p3)).astype(np.float32))
+    b3 = np.zeros(p3); b3[:9] = rng.uniform(0.5, 1.5, size=9)
+    y3 = (0.3 + x3 @ b3 + rng.normal(size=n3)).astype(np.float32)
+    lam3 = [0.2, 0.05]
+    ref3 = admm_b200.admm_lasso(x3, y3).penalty(lam3).parallel(world).opts(maxit=4000).fit()
+    s0, sn = D.row_block(n3, world, rank)
+    X3d = torch.from_numpy(np.ascontiguousarray(x3[s0:s0 + sn].T)).cuda()      # (p, rows): the (rows, p) column-major block
+    y3d = torch.from_numpy(y3[s0:s0 + sn].copy()).cuda()
+
     D.init_comm()
+    f3 = admm_b200.admm_lasso(X3d.t(), y3d).penalty(lam3).parallel(world).opts(maxit=4000).fit()
+    b3g, b3r = np.asarray(f3.beta.todense()), np.asarray(ref3.beta.todense())
+    assert np.abs(b3g - b3r).max() < 2e-4, np.abs(b3g - b3r).max()
+    assert np.abs(f3.niter.astype(int) - ref3.niter.astype(int)).max() <= max(3, 0.05 * ref3.niter.max()), (f3.niter, ref3.niter)
+    t3 = torch.from_numpy(b3g.copy()).cuda()
+    t30 = t3.clone(); dist.broadcast(t30, 0)
+    assert torch.equal(t3, t30)                                           # identical on every rank
+
     f2 = admm_b200.admm_lasso(x2s, y2s).penalty(nlambda=8).fit()          # pipelined copy + per-panel all-reduces + sharded iterations
     b2g, b2r = np.asarray(f2.beta.todense()), np.asarray(ref2.beta.todense())
     tol2 = max(2e-4, 2e-5 * np.sqrt(p2))
@@ -62,10 +82,20 @@ def main():
     assert np.allclose(f.lambda_, ref.lambda_, rtol=1e-6), (f.lambda_[:3], ref.lambda_[:3])
     assert np.abs(bg - br).max() < 2e-4, np.abs(bg - br).max()
     assert abs(int(f.niter.sum()) - int(ref.niter.sum())) <= max(3, 0.03 * int(ref.niter.sum())), (f.niter, ref.niter)
-    # replicated iterations: every rank returns the identical result
+    # sharded iterations: every rank returns the identical result ...
     t = torch.from_numpy(bg.copy()).cuda()
     t0 = t.clone(); dist.broadcast(t0, 0)
     assert torch.equal(t, t0)
+    # ... and the replicated iterations (B200ADMM_SHARD_ITER=0, one-triangle kernel on every rank) agree with them
+    os.environ["B200ADMM_SHARD_ITER"] = "0"
+    fr = admm_b200.admm_lasso(xs, ys).penalty(nlambda=15).fit()
+    del os.environ["B200ADMM_SHARD_ITER"]
+    brr = np.asarray(fr.beta.todense())
+    assert np.abs(brr - bg).max() < 1e-4, np.abs(brr - bg).max()
+    assert np.abs(fr.niter.astype(int) - f.niter.astype(int)).max() <= 2, (fr.niter, f.niter)
+    tr_ = torch.from_numpy(brr.copy()).cuda()
+    tr0 = tr_.clone(); dist.broadcast(tr0, 0)
+    assert torch.equal(tr_, tr0)
 
     fc = admm_b200.admm_lasso(xs, ys).penalty(lam_c).parallel(world).opts(maxit=4000).fit()
     bc, brc = np.asarray(fc.beta.todense()), np.asarray(ref_c.beta.todense())
