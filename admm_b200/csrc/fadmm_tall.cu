@@ -435,15 +435,38 @@ constexpr int TRI_ROWS = 4;                 // rows per step
 constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe (one float4 per thread)
 constexpr int TRI_STEP_BYTES = TRI_ROWS * TP_THREADS * 16;   // 32 KB of K^-1 per step and CTA
 
-// 16-byte global -> shared copy that bypasses the register file (src_bytes = 0: the slot is zero-filled, nothing is read)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid)
+// ---- mbarrier / bulk-copy wrappers (the ring of the one-triangle kernel) -------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int nbytes = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(gsrc), "r"(nbytes) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// contiguous global -> shared copy by the TMA unit (bytes: a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 // v[0..3] per lane -> the lanes with (lane & 7) == 0 return the warp total of row ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)
 __device__ __forceinline__ float butterfly4(float (&v)[TRI_ROWS], int lane)
@@ -467,10 +490,11 @@ __device__ __forceinline__ float butterfly4(float (&v)[TRI_ROWS], int lane)
     return v[0];
 }
 
-// NST = steps of K^-1 in flight per CTA (cp.async ring in shared memory, NST x 32 KB): the sweep is a chain of
-// ~60 steps per iteration and a step that waits for its own loads is latency-bound (measured with register loads:
-// 4.6 TB/s, 35 % of the DRAM rate busy); with the ring the loads of the next NST - 1 steps are always under way.
-// Every thread copies and later reads ONLY its own 16-byte slots, so the ring needs no barrier, just wait_group.
+// NST = steps of K^-1 in flight per CTA: a ring of NST x 32 KB in shared memory filled by the TMA unit (one elected
+// thread issues cp.async.bulk copies of whole row segments; full / empty mbarriers).  The sweep is a chain of ~60 steps per
+// iteration: with register loads every step waited for its own data (measured 4.6 TB/s, DRAM 35 % busy) and per-thread
+// cp.async cost more instructions per byte than the arithmetic itself (issue-bound); the bulk copies take the loads off
+// the instruction stream altogether.
 template <int NST>
 __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathArgs a, int vrows_per_cta, int ld)
 {
@@ -481,6 +505,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
     const int vpad = (vrows_per_cta + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
     float* xown = s_dot + TP_WARPS * 2 * vpad;           // [2 * vpad]: row sums of the own rows
     float4* ring = reinterpret_cast<float4*>(xown + 2 * vpad);   // [NST][TRI_ROWS][TP_THREADS]
+    __shared__ __align__(8) unsigned long long s_full[NST], s_empty[NST];
     __shared__ double s_sum[NSUM];
     __shared__ float s_red[TP_WARPS][NSUM];
 
@@ -513,6 +538,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
     unsigned git = 0;
     unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS, ng = ngT + ngB;
+    if (tid == 0) {
+        for (int q = 0; q < NST; q++) { mbar_init(smem_addr(&s_full[q]), 1); mbar_init(smem_addr(&s_empty[q]), TP_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int pstage = 0, cstage = 0;                          // ring positions of the producer / the consumers
+    uint32_t pphase = 0, cphase = 0;
 
     for (int k = 0; k < a.nl; k++) {
         const float lambda = (float)a.lambdas[k];
@@ -551,30 +583,37 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
                 nr = min(TRI_ROWS, (bottom ? nB : nT) - g0);
                 slot = (bottom ? vpad : 0) + g0;
             };
-            // producer cursor: (group, stripe) of the next step to put in flight
-            int pg = 0, pst = 0, pi0 = 0, pnr = 0, pslot = 0, pstage = 0;
+            // producer cursor (thread 0): (group, stripe) of the next step to put in flight
+            int pg = 0, pst = 0, pi0 = 0, pnr = 0, pslot = 0;
             if (ng > 0) group(0, pi0, pnr, pslot);
             auto issue = [&]() {
-                if (pg < ng) {
-                    const int c4 = pst * TP_THREADS + tid, j0 = 4 * c4;
-                    float4* dst = ring + (size_t)pstage * TRI_ROWS * TP_THREADS + tid;
+                if (pg >= ng) return;
+                mbar_wait(smem_addr(&s_empty[pstage]), pphase ^ 1u);          // all warps are done with this slot
+                const uint32_t fb = smem_addr(&s_full[pstage]);
+                const int off4 = pst * TP_THREADS;                              // first float4 of the stripe
+                uint32_t n4[TRI_ROWS], total = 0;
 #pragma unroll
-                    for (int r = 0; r < TRI_ROWS; r++) {
-                        const bool valid = r < pnr && j0 <= pi0 + r;
-                        cp_async16(dst + r * TP_THREADS, valid ? (a.Kinv + (size_t)(pi0 + r) * ld + j0) : a.Kinv, valid);
-                    }
-                    pst++;
-                    if (pst * TRI_STRIPE > pi0 + pnr - 1) {          // stripe starts beyond the group's longest row
-                        pst = 0; pg++;
-                        if (pg < ng) group(pg, pi0, pnr, pslot);
-                    }
+                for (int r = 0; r < TRI_ROWS; r++) {
+                    const int len4 = r < pnr ? ((pi0 + r) >> 2) + 1 - off4 : 0; // float4s of row (pi0 + r)'s prefix in this stripe
+                    n4[r] = (uint32_t)max(0, min(TP_THREADS, len4));
+                    total += n4[r];
                 }
-                cp_async_commit();                                    // (an empty group once the sweep is exhausted)
-                pstage = pstage + 1 == NST ? 0 : pstage + 1;
-            };
+                mbar_expect_tx(fb, total * 16u);
+                const uint32_t dst = smem_addr(ring + (size_t)pstage * TRI_ROWS * TP_THREADS);
 #pragma unroll
-            for (int q = 0; q < NST - 1; q++) issue();
-            int cstage = 0;
+                for (int r = 0; r < TRI_ROWS; r++)
+                    if (n4[r]) bulk_load(dst + (uint32_t)r * TP_THREADS * 16u, a.Kinv + (size_t)(pi0 + r) * ld + 4 * (size_t)off4, n4[r] * 16u, fb);
+                if (++pstage == NST) { pstage = 0; pphase ^= 1u; }
+                pst++;
+                if (pst * TRI_STRIPE > pi0 + pnr - 1) {                         // the next stripe starts beyond the longest row
+                    pst = 0; pg++;
+                    if (pg < ng) group(pg, pi0, pnr, pslot);
+                }
+            };
+            if (tid == 0) {
+#pragma unroll
+                for (int q = 0; q < NST - 1; q++) issue();
+            }
             for (int gg = 0; gg < ng; gg++) {
                 int i0, nr, slot;
                 group(gg, i0, nr, slot);
@@ -583,44 +622,50 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
 #pragma unroll
                 for (int r = 0; r < TRI_ROWS; r++) { d[r] = 0.f; ri[r] = r < nr ? rhs[i0 + r] : 0.f; }
                 for (int st = 0; st * TRI_STRIPE <= imax; st++) {
-                    issue();
-                    cp_async_wait<NST - 1>();
+                    if (tid == 0) issue();
+                    mbar_wait(smem_addr(&s_full[cstage]), cphase);
                     const int c4 = st * TP_THREADS + tid, j0 = 4 * c4;
                     const float4* src = ring + (size_t)cstage * TRI_ROWS * TP_THREADS + tid;
-                    cstage = cstage + 1 == NST ? 0 : cstage + 1;
-                    if (j0 > imax) continue;                           // (slots were zero-filled; nothing to add)
-                    float4 q[TRI_ROWS];
+                    if (j0 <= imax) {
+                        const float4 rj = reinterpret_cast<const float4*>(rhs)[c4];
+                        float4 av = reinterpret_cast<float4*>(acc)[c4];
+                        if (j0 + 3 < i0) {
+                            // all four columns lie strictly below the diagonal for every row of the group
 #pragma unroll
-                    for (int r = 0; r < TRI_ROWS; r++) q[r] = src[r * TP_THREADS];
-                    const float4 rj = reinterpret_cast<const float4*>(rhs)[c4];
-                    float4 av = reinterpret_cast<float4*>(acc)[c4];
-                    if (j0 + 3 < i0) {
-                        // all four columns lie strictly below the diagonal for every row of the group
+                            for (int r = 0; r < TRI_ROWS; r++) {
+                                if (r < nr) {
+                                    const float4 q = src[r * TP_THREADS];
+                                    d[r] = fmaf(q.x, rj.x, d[r]); d[r] = fmaf(q.y, rj.y, d[r]);
+                                    d[r] = fmaf(q.z, rj.z, d[r]); d[r] = fmaf(q.w, rj.w, d[r]);
+                                    av.x = fmaf(q.x, ri[r], av.x); av.y = fmaf(q.y, ri[r], av.y);
+                                    av.z = fmaf(q.z, ri[r], av.z); av.w = fmaf(q.w, ri[r], av.w);
+                                }
+                            }
+                        } else {
+                            // the stripe holds the diagonal: entries beyond it (and slots no copy has filled) are masked
 #pragma unroll
-                        for (int r = 0; r < TRI_ROWS; r++) {
-                            d[r] = fmaf(q[r].x, rj.x, d[r]); d[r] = fmaf(q[r].y, rj.y, d[r]);
-                            d[r] = fmaf(q[r].z, rj.z, d[r]); d[r] = fmaf(q[r].w, rj.w, d[r]);
-                            av.x = fmaf(q[r].x, ri[r], av.x); av.y = fmaf(q[r].y, ri[r], av.y);
-                            av.z = fmaf(q[r].z, ri[r], av.z); av.w = fmaf(q[r].w, ri[r], av.w);
+                            for (int r = 0; r < TRI_ROWS; r++) {
+                                const int i = i0 + r;
+                                if (r < nr && j0 <= i) {
+                                    const float4 q = src[r * TP_THREADS];
+                                    const float qx = q.x, qy = j0 + 1 <= i ? q.y : 0.f;
+                                    const float qz = j0 + 2 <= i ? q.z : 0.f, qw = j0 + 3 <= i ? q.w : 0.f;
+                                    d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
+                                    d[r] = fmaf(qz, rj.z, d[r]); d[r] = fmaf(qw, rj.w, d[r]);
+                                    av.x = fmaf(j0 < i ? qx : 0.f, ri[r], av.x); av.y = fmaf(j0 + 1 < i ? qy : 0.f, ri[r], av.y);
+                                    av.z = fmaf(j0 + 2 < i ? qz : 0.f, ri[r], av.z); av.w = fmaf(j0 + 3 < i ? qw : 0.f, ri[r], av.w);
+                                }
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < TRI_ROWS; r++) {
-                            const int i = i0 + r;                              // rows beyond nr arrive as zeros
-                            const float qx = j0 <= i ? q[r].x : 0.f, qy = j0 + 1 <= i ? q[r].y : 0.f;
-                            const float qz = j0 + 2 <= i ? q[r].z : 0.f, qw = j0 + 3 <= i ? q[r].w : 0.f;
-                            d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
-                            d[r] = fmaf(qz, rj.z, d[r]); d[r] = fmaf(qw, rj.w, d[r]);
-                            av.x = fmaf(j0 < i ? qx : 0.f, ri[r], av.x); av.y = fmaf(j0 + 1 < i ? qy : 0.f, ri[r], av.y);
-                            av.z = fmaf(j0 + 2 < i ? qz : 0.f, ri[r], av.z); av.w = fmaf(j0 + 3 < i ? qw : 0.f, ri[r], av.w);
-                        }
+                        reinterpret_cast<float4*>(acc)[c4] = av;
                     }
-                    reinterpret_cast<float4*>(acc)[c4] = av;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_addr(&s_empty[cstage]));    // this warp is done with the slot
+                    if (++cstage == NST) { cstage = 0; cphase ^= 1u; }
                 }
                 const float tot = butterfly4(d, lane);
                 if ((lane & 7) == 0) s_dot[warp * 2 * vpad + slot + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
             }
-            cp_async_wait<0>();
             // the CTA's partial column sums -> global (every thread stores the slots it owns)
             {
                 float4* dst = reinterpret_cast<float4*>(part + (size_t)cta * ld);
