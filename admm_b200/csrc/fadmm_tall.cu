@@ -430,72 +430,43 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
 // Everything is summed in a fixed order: runs are bit-reproducible; against tall_path_kernel only the summation order of
 // the K^-1 product differs.  Needs 2 p floats of shared memory (rhs + column sums): p <= ~25 000; row-sharded runs keep
 // tall_path_kernel (their exchange is per row block).
+// Measured at p = 1e4 (profiles/r2k_*, r2l_*): DRAM reads per iteration 328 MB -> 134 MB (half the matrix, and the snake
+// sweep keeps a larger share of it in the 126 MB L2), iteration 66.3 -> 58.6 us.  The gain is smaller than the byte count
+// because neither kernel is HBM-bound at the clock the iteration phase runs at in a whole fit (~1.4 GHz right after the
+// power-capped Gram): an SM takes in ~34 B / cycle from L2 (full-row kernel: 400 MB in 84.5 k cycles = 32 B / cycle / SM),
+// and this sweep spends two FMAs per element plus the row-sum butterflies.  Two ring-buffered variants of phase [A]
+// (per-thread cp.async, TMA bulk copies with full / empty mbarriers; git history) were slower: 63 and 75 us.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TRI_ROWS = 4;                 // rows per step
-constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe (one float4 per thread)
-constexpr int TRI_STEP_BYTES = TRI_ROWS * TP_THREADS * 16;   // 32 KB of K^-1 per step and CTA
+constexpr int TRI_ROWS = 8;                 // rows per group (loads in flight per thread)
+constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe
 
-// ---- mbarrier / bulk-copy wrappers (the ring of the one-triangle kernel) -------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-// contiguous global -> shared copy by the TMA unit (bytes: a multiple of 16), completion counted on `bar`
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// v[0..3] per lane -> the lanes with (lane & 7) == 0 return the warp total of row ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)
-__device__ __forceinline__ float butterfly4(float (&v)[TRI_ROWS], int lane)
+// v[0..7] per lane -> the lanes with (lane & 3) == 0 return the warp total of row ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+__device__ __forceinline__ float butterfly8(float (&v)[TRI_ROWS], int lane)
 {
     const unsigned full = 0xffffffffu;
-    const bool h16 = lane & 16, h8 = lane & 8;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const float send = h16 ? v[k] : v[k + 2];
-        const float keep = h16 ? v[k + 2] : v[k];
+    for (int k = 0; k < 4; k++) {
+        const float send = h16 ? v[k] : v[k + 4];
+        const float keep = h16 ? v[k + 4] : v[k];
         v[k] = keep + __shfl_xor_sync(full, send, 16);
     }
-    {
-        const float send = h8 ? v[0] : v[1];
-        const float keep = h8 ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(full, send, 8);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float send = h8 ? v[k] : v[k + 2];
+        const float keep = h8 ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(full, send, 8);
     }
-    v[0] += __shfl_xor_sync(full, v[0], 4);
+    {
+        const float send = h4 ? v[0] : v[1];
+        const float keep = h4 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 4);
+    }
     v[0] += __shfl_xor_sync(full, v[0], 2);
     v[0] += __shfl_xor_sync(full, v[0], 1);
     return v[0];
 }
 
-// NST = steps of K^-1 in flight per CTA: a ring of NST x 32 KB in shared memory filled by the TMA unit (one elected
-// thread issues cp.async.bulk copies of whole row segments; full / empty mbarriers).  The sweep is a chain of ~60 steps per
-// iteration: with register loads every step waited for its own data (measured 4.6 TB/s, DRAM 35 % busy) and per-thread
-// cp.async cost more instructions per byte than the arithmetic itself (issue-bound); the bulk copies take the loads off
-// the instruction stream altogether.
-template <int NST>
 __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathArgs a, int vrows_per_cta, int ld)
 {
     extern __shared__ __align__(16) float smem[];
@@ -504,8 +475,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
     float* s_dot = acc + ld;                             // [TP_WARPS][2 * vpad]: per-warp row sums
     const int vpad = (vrows_per_cta + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
     float* xown = s_dot + TP_WARPS * 2 * vpad;           // [2 * vpad]: row sums of the own rows
-    float4* ring = reinterpret_cast<float4*>(xown + 2 * vpad);   // [NST][TRI_ROWS][TP_THREADS]
-    __shared__ __align__(8) unsigned long long s_full[NST], s_empty[NST];
     __shared__ double s_sum[NSUM];
     __shared__ float s_red[TP_WARPS][NSUM];
 
@@ -537,14 +506,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
     unsigned long long nbar = 0;
     unsigned git = 0;
     unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS, ng = ngT + ngB;
-    if (tid == 0) {
-        for (int q = 0; q < NST; q++) { mbar_init(smem_addr(&s_full[q]), 1); mbar_init(smem_addr(&s_empty[q]), TP_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    int pstage = 0, cstage = 0;                          // ring positions of the producer / the consumers
-    uint32_t pphase = 0, cphase = 0;
 
     for (int k = 0; k < a.nl; k++) {
         const float lambda = (float)a.lambdas[k];
@@ -574,97 +535,56 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
             // ---- [A] lower-triangle sweep of the own rows --------------------------------------------
             for (int v = tid; v < nvec; v += TP_THREADS) reinterpret_cast<float4*>(acc)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool rev = a.snake && (git & 1u);
-            // group gg of the sweep (4 rows of one block): first row, rows, slot of its row sums
-            auto group = [&](int gg, int& i0, int& nr, int& slot) {
-                const int g = rev ? (ng - 1 - gg) : gg;
+            const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS;
+            for (int gg = 0; gg < ngT + ngB; gg++) {
+                const int g = rev ? (ngT + ngB - 1 - gg) : gg;
                 const bool bottom = g >= ngT;
-                const int g0 = (bottom ? g - ngT : g) * TRI_ROWS;
-                i0 = (bottom ? b0 : t0) + g0;
-                nr = min(TRI_ROWS, (bottom ? nB : nT) - g0);
-                slot = (bottom ? vpad : 0) + g0;
-            };
-            // producer cursor (thread 0): (group, stripe) of the next step to put in flight
-            int pg = 0, pst = 0, pi0 = 0, pnr = 0, pslot = 0;
-            if (ng > 0) group(0, pi0, pnr, pslot);
-            auto issue = [&]() {
-                if (pg >= ng) return;
-                mbar_wait(smem_addr(&s_empty[pstage]), pphase ^ 1u);          // all warps are done with this slot
-                const uint32_t fb = smem_addr(&s_full[pstage]);
-                const int off4 = pst * TP_THREADS;                              // first float4 of the stripe
-                uint32_t n4[TRI_ROWS], total = 0;
-#pragma unroll
-                for (int r = 0; r < TRI_ROWS; r++) {
-                    const int len4 = r < pnr ? ((pi0 + r) >> 2) + 1 - off4 : 0; // float4s of row (pi0 + r)'s prefix in this stripe
-                    n4[r] = (uint32_t)max(0, min(TP_THREADS, len4));
-                    total += n4[r];
-                }
-                mbar_expect_tx(fb, total * 16u);
-                const uint32_t dst = smem_addr(ring + (size_t)pstage * TRI_ROWS * TP_THREADS);
-#pragma unroll
-                for (int r = 0; r < TRI_ROWS; r++)
-                    if (n4[r]) bulk_load(dst + (uint32_t)r * TP_THREADS * 16u, a.Kinv + (size_t)(pi0 + r) * ld + 4 * (size_t)off4, n4[r] * 16u, fb);
-                if (++pstage == NST) { pstage = 0; pphase ^= 1u; }
-                pst++;
-                if (pst * TRI_STRIPE > pi0 + pnr - 1) {                         // the next stripe starts beyond the longest row
-                    pst = 0; pg++;
-                    if (pg < ng) group(pg, pi0, pnr, pslot);
-                }
-            };
-            if (tid == 0) {
-#pragma unroll
-                for (int q = 0; q < NST - 1; q++) issue();
-            }
-            for (int gg = 0; gg < ng; gg++) {
-                int i0, nr, slot;
-                group(gg, i0, nr, slot);
+                const int g0 = (bottom ? g - ngT : g) * TRI_ROWS;              // first row of the group within its block
+                const int blk0 = bottom ? b0 : t0, blkn = bottom ? nB : nT;
+                const int i0 = blk0 + g0;                                      // smallest row of the group
+                const int nr = min(TRI_ROWS, blkn - g0);
                 const int imax = i0 + nr - 1;
                 float d[TRI_ROWS], ri[TRI_ROWS];
 #pragma unroll
                 for (int r = 0; r < TRI_ROWS; r++) { d[r] = 0.f; ri[r] = r < nr ? rhs[i0 + r] : 0.f; }
-                for (int st = 0; st * TRI_STRIPE <= imax; st++) {
-                    if (tid == 0) issue();
-                    mbar_wait(smem_addr(&s_full[cstage]), cphase);
-                    const int c4 = st * TP_THREADS + tid, j0 = 4 * c4;
-                    const float4* src = ring + (size_t)cstage * TRI_ROWS * TP_THREADS + tid;
-                    if (j0 <= imax) {
-                        const float4 rj = reinterpret_cast<const float4*>(rhs)[c4];
-                        float4 av = reinterpret_cast<float4*>(acc)[c4];
-                        if (j0 + 3 < i0) {
-                            // all four columns lie strictly below the diagonal for every row of the group
+                const float* kbase = a.Kinv + (size_t)i0 * ld;
+                for (int c4 = tid; 4 * c4 <= imax; c4 += TP_THREADS) {
+                    const int j0 = 4 * c4;
+                    float4 q[TRI_ROWS];
 #pragma unroll
-                            for (int r = 0; r < TRI_ROWS; r++) {
-                                if (r < nr) {
-                                    const float4 q = src[r * TP_THREADS];
-                                    d[r] = fmaf(q.x, rj.x, d[r]); d[r] = fmaf(q.y, rj.y, d[r]);
-                                    d[r] = fmaf(q.z, rj.z, d[r]); d[r] = fmaf(q.w, rj.w, d[r]);
-                                    av.x = fmaf(q.x, ri[r], av.x); av.y = fmaf(q.y, ri[r], av.y);
-                                    av.z = fmaf(q.z, ri[r], av.z); av.w = fmaf(q.w, ri[r], av.w);
-                                }
-                            }
-                        } else {
-                            // the stripe holds the diagonal: entries beyond it (and slots no copy has filled) are masked
+                    for (int r = 0; r < TRI_ROWS; r++)
+                        q[r] = (r < nr && j0 <= i0 + r) ? ld_stream_f4(reinterpret_cast<const float4*>(kbase + (size_t)r * ld) + c4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 rj = reinterpret_cast<const float4*>(rhs)[c4];
+                    float4 av = reinterpret_cast<float4*>(acc)[c4];
+                    if (j0 + 3 < i0) {
+                        // all four columns lie strictly below the diagonal for every row of the group
 #pragma unroll
-                            for (int r = 0; r < TRI_ROWS; r++) {
-                                const int i = i0 + r;
-                                if (r < nr && j0 <= i) {
-                                    const float4 q = src[r * TP_THREADS];
-                                    const float qx = q.x, qy = j0 + 1 <= i ? q.y : 0.f;
-                                    const float qz = j0 + 2 <= i ? q.z : 0.f, qw = j0 + 3 <= i ? q.w : 0.f;
-                                    d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
-                                    d[r] = fmaf(qz, rj.z, d[r]); d[r] = fmaf(qw, rj.w, d[r]);
-                                    av.x = fmaf(j0 < i ? qx : 0.f, ri[r], av.x); av.y = fmaf(j0 + 1 < i ? qy : 0.f, ri[r], av.y);
-                                    av.z = fmaf(j0 + 2 < i ? qz : 0.f, ri[r], av.z); av.w = fmaf(j0 + 3 < i ? qw : 0.f, ri[r], av.w);
-                                }
-                            }
+                        for (int r = 0; r < TRI_ROWS; r++) {
+                            d[r] = fmaf(q[r].x, rj.x, d[r]); d[r] = fmaf(q[r].y, rj.y, d[r]);
+                            d[r] = fmaf(q[r].z, rj.z, d[r]); d[r] = fmaf(q[r].w, rj.w, d[r]);
+                            av.x = fmaf(q[r].x, ri[r], av.x); av.y = fmaf(q[r].y, ri[r], av.y);
+                            av.z = fmaf(q[r].z, ri[r], av.z); av.w = fmaf(q[r].w, ri[r], av.w);
                         }
-                        reinterpret_cast<float4*>(acc)[c4] = av;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < TRI_ROWS; r++) {
+                            const int i = i0 + r;                              // rows beyond nr were loaded as zeros
+                            const float qx = j0 <= i ? q[r].x : 0.f, qy = j0 + 1 <= i ? q[r].y : 0.f;
+                            const float qz = j0 + 2 <= i ? q[r].z : 0.f, qw = j0 + 3 <= i ? q[r].w : 0.f;
+                            d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
+                            d[r] = fmaf(qz, rj.z, d[r]); d[r] = fmaf(qw, rj.w, d[r]);
+                            av.x = fmaf(j0 < i ? qx : 0.f, ri[r], av.x); av.y = fmaf(j0 + 1 < i ? qy : 0.f, ri[r], av.y);
+                            av.z = fmaf(j0 + 2 < i ? qz : 0.f, ri[r], av.z); av.w = fmaf(j0 + 3 < i ? qw : 0.f, ri[r], av.w);
+                        }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_addr(&s_empty[cstage]));    // this warp is done with the slot
-                    if (++cstage == NST) { cstage = 0; cphase ^= 1u; }
+                    reinterpret_cast<float4*>(acc)[c4] = av;
                 }
-                const float tot = butterfly4(d, lane);
-                if ((lane & 7) == 0) s_dot[warp * 2 * vpad + slot + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
+                const float tot = butterfly8(d, lane);
+                if ((lane & 3) == 0) {
+                    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    s_dot[warp * 2 * vpad + (bottom ? vpad : 0) + g0 + r] = tot;
+                }
             }
             // the CTA's partial column sums -> global (every thread stores the slots it owns)
             {
@@ -888,8 +808,8 @@ size_t tall_state_floats(int p)
     return 8 * ld + 2 * (size_t)2048 * PART_STRIDE;          // partial slots: up to 8 ranks x 148 CTAs, double-buffered
 }
 
-// grid of the one-triangle kernel: folded rows per CTA, ring depth and the grid size (0: the shape does not take this path)
-static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes, int* nst)
+// grid of the one-triangle kernel: folded rows per CTA and the grid size (0: the shape does not take this path)
+static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes)
 {
     const int ld = (p + 3) & ~3;
     const int V = (p + 1) / 2;
@@ -898,16 +818,13 @@ static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes, int*
     G = (V + vr - 1) / vr;
     const int vpad = (vr + TRI_ROWS - 1) / TRI_ROWS * TRI_ROWS;
     *vrows_per_cta = vr;
-    const size_t fixed = sizeof(float) * (2 * (size_t)ld + (size_t)(TP_WARPS + 1) * 2 * vpad);
-    const size_t budget = 225 * 1024;
-    *nst = fixed + 4 * (size_t)TRI_STEP_BYTES <= budget ? 4 : (fixed + 2 * (size_t)TRI_STEP_BYTES <= budget ? 2 : 0);
-    *smem_bytes = fixed + (size_t)*nst * TRI_STEP_BYTES;
-    return *nst ? G : 0;
+    *smem_bytes = sizeof(float) * (2 * (size_t)ld + (size_t)(TP_WARPS + 1) * 2 * vpad);
+    return (*smem_bytes <= 200 * 1024) ? G : 0;
 }
 size_t tall_tri_part_floats(int p)
 {
-    int vr, nst; size_t sm;
-    const int G = tri_grid(p, sm_count(), &vr, &sm, &nst);
+    int vr; size_t sm;
+    const int G = tri_grid(p, sm_count(), &vr, &sm);
     return G > 0 ? (size_t)G * (size_t)((p + 3) & ~3) : 0;
 }
 
@@ -917,23 +834,21 @@ int launch_tall_path(cudaStream_t s, const TallPathArgs& a)
     const int ld = (p + 3) & ~3;
     const int sms = sm_count();
     if (a.tri_part != nullptr && a.nranks <= 1) {
-        int vr, nst; size_t smem;
-        const int G = tri_grid(p, sms, &vr, &smem, &nst);
+        int vr; size_t smem;
+        const int G = tri_grid(p, sms, &vr, &smem);
         if (G > 0) {
-            const void* fn = nst == 4 ? (const void*)tall_path_tri_kernel<4> : (const void*)tall_path_tri_kernel<2>;
-            static size_t tri_smem_set[2] = {0, 0};
-            size_t& set = tri_smem_set[nst == 4 ? 1 : 0];
-            if (smem > set) {
-                CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                set = smem;
+            static size_t tri_smem_set = 0;
+            if (smem > tri_smem_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(tall_path_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                tri_smem_set = smem;
             }
             int occ = 0;
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TP_THREADS, smem));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tall_path_tri_kernel, TP_THREADS, smem));
             if (occ < 1) throw CudaError("tall path (triangle) kernel does not fit on an SM");
             TallPathArgs args = a;
             int vri = vr, ldi = ld;
             void* params[] = { (void*)&args, (void*)&vri, (void*)&ldi };
-            CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(TP_THREADS), params, smem, s));
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tall_path_tri_kernel, dim3(G), dim3(TP_THREADS), params, smem, s));
             ++g_launch_count;
             return G;
         }
