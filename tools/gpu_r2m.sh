@@ -12,7 +12,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
     > $O/r2m_bench_2gpu.json 2> $O/r2m_bench_2gpu.err
 echo "tall 2gpu rc=$?"
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 \
-    --config consensus --n 250000 --p 80000 > $O/r2m_consensus_2gpu_rehearsal.json 2> $O/r2m_consensus_2gpu_rehearsal.err
+    --config consensus --rows 250000 --cols 80000 > $O/r2m_consensus_2gpu_rehearsal.json 2> $O/r2m_consensus_2gpu_rehearsal.err
 echo "consensus rehearsal rc=$?"
 nvidia-smi --query-gpu=memory.used,memory.total --format=csv >> $O/r2m_env.txt
 tail -c 600 $O/r2m_bench_2gpu.err; tail -c 1500 $O/r2m_consensus_2gpu_rehearsal.err
