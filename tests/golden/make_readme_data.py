@@ -61,6 +61,19 @@ class RRng:
     def rnorm(self, k, mean=0.0, sd=1.0):
         return np.array([mean + sd * self.norm() for _ in range(k)])
 
+    # vectorised forms of unif / norm (the README's benchmark sections draw up to 1e7 normals)
+    def runif_vec(self, k):
+        v = self.bg.random_raw(k).astype(np.float64) * 2.3283064365386963e-10
+        i2_32m1 = 2.328306437080797e-10
+        v[v <= 0.0] = 0.5 * i2_32m1
+        v[1.0 - v <= 0.0] = 1.0 - 0.5 * i2_32m1
+        return v
+
+    def rnorm_vec(self, k, mean=0.0, sd=1.0):
+        u = self.runif_vec(2 * k)
+        big = 134217728.0
+        return mean + sd * ndtri((np.floor(big * u[0::2]) + u[1::2]) / big)
+
     def sample_old(self, v):
         v = np.asarray(v)
         m = len(v)
@@ -93,7 +106,22 @@ def bp_data():
     return x, y, beta_true
 
 
+def benchmark_data(n, p, m=100):
+    """Input of the README's timing sections (README.md:193-201 n > p, :246-254 p > n): set.seed(123);
+    b <- c(runif(m), 0 ...); x <- matrix(rnorm(n * p, sd = 2), n, p); y <- x %*% b + rnorm(n).  Generated on the fly
+    (80 MB at n = 1e4, p = 1e3), never stored."""
+    r = RRng(123)
+    b = np.concatenate([r.runif_vec(m), np.zeros(p - m)])
+    x = r.rnorm_vec(n * p, 0.0, 2.0).reshape(p, n).T.copy(order="F")
+    y = x @ b + r.rnorm_vec(n)
+    return x, y, b
+
+
 def main():
+    r = RRng(123)
+    assert np.allclose(r.runif_vec(3), [0.2875775201246142, 0.7883051354438066, 0.4089769218116999], atol=1e-15)
+    r = RRng(123)
+    assert np.allclose(r.rnorm_vec(3), [-0.56047564655221, -0.23017748948328, 1.55870831414912], atol=1e-12)
     r = RRng(123)
     u = r.runif(3)
     assert np.allclose(u, [0.2875775201246142, 0.7883051354438066, 0.4089769218116999], atol=1e-15), u
