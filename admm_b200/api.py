@@ -58,6 +58,7 @@ class ADMM_Lasso:
         self.nlambda = 100
         n, p = _shape(x)
         self.lambda_min_ratio = 0.01 if n < p else 0.0001
+        self._lmr_is_default = True
         self.nthread = 1
         self.maxit = 10000
         self.eps_abs = 1e-5
@@ -75,6 +76,9 @@ class ADMM_Lasso:
         lmr = (0.01 if n < p else 0.0001) if lambda_min_ratio is None else float(lambda_min_ratio)
         if lmr >= 1 or lmr <= 0:
             raise ValueError("lambda_min_ratio must be within (0, 1)")
+        # a default is resolved by the library from the GLOBAL row count (a rank of a row-sharded run may hold fewer
+        # rows than columns: measured on 8 ranks, 500 rows x 1100 columns each, the local default was 0.01 against 1e-4)
+        self._lmr_is_default = lambda_min_ratio is None
         self.lambda_ = lam
         self.nlambda = int(nlambda)
         self.lambda_min_ratio = lmr
@@ -107,6 +111,10 @@ class ADMM_Lasso:
     def _opts(self):
         return K.Opts(self.maxit, self.eps_abs, self.eps_rel, self.rho)
 
+    def _lmr_arg(self):
+        # 0 -> the library takes the reference's default from the global shape
+        return 0.0 if self._lmr_is_default else self.lambda_min_ratio
+
     def _lambda_args(self):
         lam = np.ascontiguousarray(self.lambda_, dtype=np.float64)
         return lam, (lam.ctypes.data if lam.size else None), int(lam.size)
@@ -121,10 +129,10 @@ class ADMM_Lasso:
         P = K.Path()
         L = K.lib()
         if self.nthread <= 1:
-            rc = L.b200admm_lasso(C.byref(d), lam_ptr, nlam, self.nlambda, self.lambda_min_ratio,
+            rc = L.b200admm_lasso(C.byref(d), lam_ptr, nlam, self.nlambda, self._lmr_arg(),
                                   int(self.standardize), int(self.intercept), C.byref(o), C.byref(P))
         else:
-            rc = L.b200admm_parlasso(C.byref(d), lam_ptr, nlam, self.nlambda, self.lambda_min_ratio,
+            rc = L.b200admm_parlasso(C.byref(d), lam_ptr, nlam, self.nlambda, self._lmr_arg(),
                                      int(self.standardize), int(self.intercept), self.nthread, C.byref(o), C.byref(P))
         K.check(rc)
         del keep
@@ -150,7 +158,7 @@ class ADMM_Enet(ADMM_Lasso):
         lam, lam_ptr, nlam = self._lambda_args()
         o = self._opts()
         P = K.Path()
-        rc = K.lib().b200admm_enet(C.byref(d), lam_ptr, nlam, self.nlambda, self.lambda_min_ratio,
+        rc = K.lib().b200admm_enet(C.byref(d), lam_ptr, nlam, self.nlambda, self._lmr_arg(),
                                    int(self.standardize), int(self.intercept), self.alpha, C.byref(o), C.byref(P))
         K.check(rc)
         del keep

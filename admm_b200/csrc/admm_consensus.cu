@@ -239,7 +239,7 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
     if (rq.nlambda_given < 1) {
         if (rq.nlambda < 1) throw ArgError("nlambda must be at least 1");
         const double lmax = lambda0 / (double)n * (double)st.scaleY;
-        make_lambda_grid(lmax, rq.lmin_ratio, rq.nlambda, lam);
+        make_lambda_grid(lmax, rq.lmin_ratio > 0 ? rq.lmin_ratio : (n < p ? 0.01 : 1e-4), rq.nlambda, lam);   // (default from the global n)
     } else {
         if (!rq.lambda_given) throw ArgError("lambda is null");
         lam.assign(rq.lambda_given, rq.lambda_given + rq.nlambda_given);

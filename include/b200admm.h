@@ -91,7 +91,8 @@ typedef struct b200admm_path {
 
 /* admm_lasso(x, y, lambda, nlambda, lmin_ratio, standardize, intercept, opts)
  * lambda_given: user lambdas sorted decreasingly by the R side (may be NULL),
- * nlambda_given < 1 -> log-linear grid of `nlambda` values down to lmin_ratio * lambda_max. */
+ * nlambda_given < 1 -> log-linear grid of `nlambda` values down to lmin_ratio * lambda_max; lmin_ratio <= 0 selects the
+ * front end's default (R/30_admm_lasso.R:44: 0.01 if n < p else 1e-4) from the GLOBAL row count of a row-sharded run. */
 int b200admm_lasso(const b200admm_data* d, const double* lambda_given, int nlambda_given,
                    int nlambda, double lmin_ratio, int standardize, int intercept,
                    const b200admm_opts* opts, b200admm_path* out);

@@ -219,6 +219,19 @@ def test_user_rho_and_nonconvergence(A, O):
     assert np.abs(dense(f.beta)[:, 0] - o["beta"][:, 0]).max() < 1e-5
 
 
+def test_default_lambda_min_ratio_is_resolved_by_the_library(A):
+    """A default lambda_min_ratio goes to the C ABI as 0 and is resolved there from the GLOBAL shape (a rank of a
+    row-sharded run can hold fewer rows than columns; tools/mgpu_bisect.py): same grid as the explicit R default."""
+    rng = np.random.default_rng(5)
+    for (n, p, ratio) in ((400, 30, 1e-4), (30, 90, 0.01)):
+        x = np.asfortranarray(rng.normal(size=(n, p)))
+        y = x[:, :3] @ np.array([1.0, -0.5, 0.25]) + 0.1 * rng.normal(size=n)
+        fd = A.admm_lasso(x, y).penalty(nlambda=7).fit()
+        fe = A.admm_lasso(x, y).penalty(nlambda=7, lambda_min_ratio=ratio).fit()
+        assert np.array_equal(fd.lambda_, fe.lambda_)
+        assert abs(fd.lambda_[-1] / fd.lambda_[0] - ratio) < 1e-9 * ratio + 1e-12
+
+
 def test_too_few_variables_is_an_error(A):
     from admm_b200 import B200AdmmError
     x, y = make_problem(50, 2, seed=1, nsig=1)
