@@ -708,6 +708,22 @@ int b200admm_k_gemm_tn_f32(const void* a, int64_t lda, const void* b, int64_t ld
     });
 }
 
+int b200admm_k_gemm_f64(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const void* a, int64_t lda,
+                        const void* b, int64_t ldb, double beta, void* c, int64_t ldc, int mode, float* ms_out, int repeats)
+{
+    return fenced([&] {
+        Context& cx = ctx();
+        if (m < 1 || n < 1 || k < 1 || !a || !b || !c) throw ArgError("gemm_f64: bad arguments");
+        const int reps = repeats < 1 ? 1 : repeats;
+        EventTimer t(cx.stream);
+        t.start();
+        for (int r = 0; r < reps; r++)
+            gemm<double>(cx.stream, ta != 0, tb != 0, m, n, k, alpha, (const double*)a, lda, (const double*)b, ldb, beta, (double*)c, ldc, mode);
+        const double sec = t.stop();
+        if (ms_out) *ms_out = (float)(sec * 1e3 / reps);
+    });
+}
+
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host)
 {
     return fenced([&] {

@@ -219,6 +219,12 @@ int b200admm_k_coarse_eig_f32(const void* s, int64_t n, float* ev_host, int* inf
  * 2 C = -A'B.  The building block of the blocked factorisation (kernels.h: gemm_tn_tensor). */
 int b200admm_k_gemm_tn_f32(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
                            void* c, int64_t ldc, int tile_mode, int klo_mode, int khi_mode, int epi);
+/* C (m x n, ldc) = alpha op(A) op(B) + beta C in float64 (device, column-major): the product behind the LAD / BP Gram
+ * matrices and triangular solves (dsyrk_ / dtrsm_ in src/ADMMLAD.h:186-201, src/ADMMBP.h:167-182).  mode: bit 0 store i >= j
+ * only, bit 1 mirror, bits 2-5 triangular operands (kernels.h: GEMM_*).  Tensor-core (mma.sync f64) tiles when the
+ * 128 x 128 grid fills the chip, CUDA-core tiles otherwise.  ms_out (optional): kernel time of `repeats` launches / repeats. */
+int b200admm_k_gemm_f64(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const void* a, int64_t lda,
+                        const void* b, int64_t ldb, double beta, void* c, int64_t ldc, int mode, float* ms_out, int repeats);
 int b200admm_k_chol_f32(void* a, int64_t p, int* info_host);                 /* lower, in place */
 int b200admm_k_spd_inverse_f32(void* a, int64_t p, void* work, int* info_host); /* a <- a^-1 (full) */
 /* fused z + u + residual + norms pass of the accelerated loop on vectors of length len

@@ -312,3 +312,56 @@ def test_tensor_core_tn_product(K, torch, M, N, Kd, tile_mode, klo, khi, epi):
     assert torch.equal(Cd[:, M:], C0[:, M:])
     if tile_mode != 0:
         assert torch.equal(Cd[:, :M][~mask], C0[:, :M][~mask])
+
+
+@pytest.mark.parametrize("ta,tb,M,N,Kd,mode", [
+    (1, 0, 1700, 1700, 3000, 3),        # X'X lower + mirror (LAD Gram): tensor-core tiles (14 x 14 >= 148)
+    (0, 1, 1664, 1664, 2111, 3),        # A A' lower + mirror (BP Gram)
+    (0, 0, 2000, 1900, 2000, 4),        # op(A) = A lower triangular (M = L^-1 A panels)
+    (0, 1, 1800, 1700, 1700, 32),       # op(B) = B', B lower triangular
+    (1, 0, 1900, 1800, 1900, 8),        # op(A) = A', A lower triangular
+    (0, 0, 1800, 1700, 1800, 16),       # op(B) = B lower triangular
+    (1, 1, 1601, 1555, 1033, 0),        # plain, ragged edges
+    (0, 0, 300, 200, 150, 0),           # small: CUDA-core tiles
+])
+def test_gemm_f64_all_modes(K, torch, ta, tb, M, N, Kd, mode):
+    """float64 product behind the LAD / BP setup (tensor-core mma.sync.f64 tiles when the grid fills the chip) against
+    NumPy float64, every transposition / triangular-operand / lower-mirror mode; alpha, beta != trivial."""
+    rng = np.random.default_rng(M + N + Kd + mode)
+    a = rng.normal(size=(Kd, M) if ta else (M, Kd))
+    b = rng.normal(size=(N, Kd) if tb else (Kd, N))
+    opa = a.T if ta else a
+    opb = b.T if tb else b
+    if mode & 4:
+        a = np.tril(a); opa = a
+    if mode & 8:
+        a = np.tril(a); opa = a.T
+    if mode & 16:
+        b = np.tril(b); opb = b
+    if mode & 32:
+        b = np.tril(b); opb = b.T
+    c0 = rng.normal(size=(M, N))
+    alpha, beta = 0.75, (0.0 if mode & 3 else -0.5)
+    ref = alpha * (opa @ opb) + beta * c0
+    # triangular operands: the kernel must not read the structurally-zero half -> poison it
+    a_dev, b_dev = a.copy(), b.copy()
+    if mode & (4 | 8):
+        a_dev[np.triu_indices_from(a_dev, 1)] = np.nan
+    if mode & (16 | 32):
+        b_dev[np.triu_indices_from(b_dev, 1)] = np.nan
+    ad = torch.from_numpy(np.ascontiguousarray(a_dev.T)).cuda()       # column-major on the device
+    bd = torch.from_numpy(np.ascontiguousarray(b_dev.T)).cuda()
+    cd = torch.from_numpy(np.ascontiguousarray(c0.T)).cuda()
+    torch.cuda.synchronize()
+    K.check(K.lib().b200admm_k_gemm_f64(ta, tb, M, N, Kd, alpha, ad.data_ptr(), a.shape[0], bd.data_ptr(), b.shape[0], beta,
+                                        cd.data_ptr(), M, mode, None, 1))
+    got = cd.cpu().numpy().T
+    if mode & 1:                        # lower (+ mirror): square C
+        if mode & 2:
+            assert np.array_equal(got, got.T)
+            assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max()
+        else:
+            il = np.tril_indices(M)
+            assert np.abs(got[il] - ref[il]).max() < 1e-11 * np.abs(ref).max()
+    else:
+        assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max()
