@@ -330,6 +330,8 @@ def test_gemm_f64_all_modes(K, torch, ta, tb, M, N, Kd, mode):
     rng = np.random.default_rng(M + N + Kd + mode)
     a = rng.normal(size=(Kd, M) if ta else (M, Kd))
     b = rng.normal(size=(N, Kd) if tb else (Kd, N))
+    if mode & 1:
+        b = a.copy()                    # lower / mirror stores are for symmetric products (X'X, A A')
     opa = a.T if ta else a
     opb = b.T if tb else b
     if mode & 4:
