@@ -23,6 +23,7 @@
 // Compiled with --fmad=false (unfused, reference order).
 #include "solvers.h"
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -105,6 +106,90 @@ __global__ void __launch_bounds__(WT) wide_active_kernel(const float* __restrict
         const float d = warp_sum((s0 + s1) + (s2 + s3));
         if (lane == 0) x[j] = prox_active(x[j] - d, q);
     }
+}
+
+// ---- screened regular step -----------------------------------------------------------------------------
+// A regular step evaluates x_j = prox(-X_j' tmp / gamma + x_j) for ALL p columns although all but a few thousand of them
+// come out zero: 4 n p bytes (40 GB at C3) per step, 413 times per path.  The screen reads an fp16 copy of the design
+// (2 n p bytes) and proves most of them zero without touching the float32 data:
+//     S_j = sum_i fp16(x_ij) tmp_i  (float32 accumulation),     |V_j - S_j| <= E_j
+// where V_j is the value gemv_t computes and
+//     E_j = [ (2^-11 + 2 g (1 + 2^-11)) |x_j|_2 + 2^-25 sqrt(n) ] |tmp|_2 * 1.001,    g = (n / 32 + 16) 2^-24
+// (fp16 rounding of a normal number <= 2^-11 relative, of a subnormal <= 2^-25 absolute; g bounds the accumulated rounding
+// of either float32 dot product: no sum runs over more than n / 32 + 16 sequential additions; Cauchy-Schwarz; 1.001 covers
+// the float32 norms).  A column with x_j = 0 and (|S_j| + E_j) <= thr (1 - 1e-6), thr = gamma * (prox threshold), stays
+// exactly zero in the unscreened computation too (|fl(-V_j / gamma)| <= threshold); every other column -- the current
+// support and the few per mille near the threshold -- is recomputed from the float32 data with gemv_t's own summation
+// order (gemv_t_list).  The step is therefore bit-identical to the unscreened one (tests: B200ADMM_WIDE_SCREEN=0).
+__global__ void __launch_bounds__(WT) wide_half_copy_kernel(const float* __restrict__ X, i64 ldx, i64 n, i64 p, i64 ldh,
+                                                            __half* __restrict__ Xh, float* __restrict__ colnorm)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 nwarps = (i64)gridDim.x * (WT >> 5);
+    for (i64 j = (i64)blockIdx.x * (WT >> 5) + (threadIdx.x >> 5); j < p; j += nwarps) {
+        const float* col = X + j * ldx;
+        __half* dst = Xh + j * ldh;
+        float s = 0.f;
+        for (i64 i = lane; i < ldh; i += 32) {
+            const float v = i < n ? col[i] : 0.f;
+            dst[i] = __float2half_rn(v);
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) colnorm[j] = sqrtf(s);
+    }
+}
+// out[0] = |v|_2 (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) wide_norm2_kernel(const float* __restrict__ v, i64 n, float* __restrict__ out)
+{
+    __shared__ float scratch[33];
+    float s = 0.f;
+    for (i64 i = threadIdx.x; i < n; i += 1024) s = fmaf(v[i], v[i], s);
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[0] = sqrtf(s);
+}
+// mark[j] = 1 if column j must be evaluated exactly, 0 if it provably stays zero
+__global__ void __launch_bounds__(WT) wide_screen_kernel(const __half* __restrict__ Xh, i64 ldh, i64 n, i64 p, const float* __restrict__ tmp,
+                                                         const float* __restrict__ x, const float* __restrict__ colnorm,
+                                                         const float* __restrict__ tmpnorm, float kx, float kn, float thr_safe,
+                                                         float* __restrict__ mark)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 nwarps = (i64)gridDim.x * (WT >> 5);
+    const float tn = *tmpnorm;
+    const i64 nv = ldh / 8;                                  // 16-byte groups of 8 halves per column
+    for (i64 j = (i64)blockIdx.x * (WT >> 5) + (threadIdx.x >> 5); j < p; j += nwarps) {
+        if (x[j] != 0.f) { if (lane == 0) mark[j] = 1.f; continue; }
+        const uint4* col = reinterpret_cast<const uint4*>(Xh + j * ldh);
+        float s0 = 0.f, s1 = 0.f;
+        for (i64 g = lane; g < nv; g += 32) {
+            uint4 h;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(col + g));
+            const i64 i0 = g * 8;
+            float t[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) t[e] = i0 + e < n ? tmp[i0 + e] : 0.f;
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+            s0 = fmaf(a.x, t[0], s0); s1 = fmaf(a.y, t[1], s1); s0 = fmaf(b.x, t[2], s0); s1 = fmaf(b.y, t[3], s1);
+            s0 = fmaf(c.x, t[4], s0); s1 = fmaf(c.y, t[5], s1); s0 = fmaf(d.x, t[6], s0); s1 = fmaf(d.y, t[7], s1);
+        }
+        const float sj = warp_sum(s0 + s1);
+        if (lane == 0) {
+            const float e = (kx * colnorm[j] + kn) * tn;
+            mark[j] = (fabsf(sj) + e <= thr_safe) ? 0.f : 1.f;
+        }
+    }
+}
+// x_j = prox(-vec_j / gamma + x_j) for the listed columns
+__global__ void __launch_bounds__(WT) wide_prox_list_kernel(const float* __restrict__ vec, const int* __restrict__ list, int count,
+                                                            float* __restrict__ x, float gamma, WideProx q)
+{
+    const int k = blockIdx.x * WT + threadIdx.x;
+    if (k >= count) return;
+    const int j = list[k];
+    const float v = -vec[j] / gamma + x[j];
+    x[j] = prox_regular(v, q);
 }
 
 // ---- stable compaction of "x[j] != 0" into a sorted index list ---------------------------------
@@ -430,6 +515,26 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     }
     const int nl = (int)lam.size();
 
+    // ---- fp16 copy + column norms for the screened regular steps (see wide_screen_kernel) -----------------------
+    const char* screen_env = getenv("B200ADMM_WIDE_SCREEN");
+    const bool screen = !(screen_env && !strcmp(screen_env, "0")) && gemv_t_uses_warp_kernel(n) && p >= 4096 && p < 2147483647LL;
+    const i64 ldh = (n + 7) & ~(i64)7;
+    DevBuf<__half> Xh;
+    DevBuf<float> colnorm, tmpnorm;
+    DevBuf<int> cand;
+    if (screen) {
+        tm.start();
+        Xh.alloc((size_t)ldh * (size_t)p); colnorm.alloc(p); tmpnorm.alloc(1); cand.alloc(p);
+        wide_half_copy_kernel<<<(unsigned)std::min<i64>((p + 7) / 8, (i64)sm_count() * 16), WT, 0, s>>>(X, ldx, n, p, ldh, Xh.p, colnorm.p);
+        KERNEL_CHECK();
+        T.factor = tm.stop();                                   // (reported under `factor`: the wide path has no factorisation)
+    }
+    const double g_round = ((double)n / 32.0 + 16.0) * std::ldexp(1.0, -24);
+    const float screen_kx = (float)((std::ldexp(1.0, -11) + 2.0 * g_round * (1.0 + std::ldexp(1.0, -11))) * 1.001);
+    const float screen_kn = (float)(std::ldexp(1.0, -25) * std::sqrt((double)n) * 1.001);
+    double screened_steps = 0, screened_cand = 0;
+    int last_ncand = 0;
+
     // ---- state ---------------------------------------------------------------------------------------
     DevBuf<float> x(p), Ax(n), z(n), y(n), tmp(n);
     DevBuf<int> supp[2], nnz_dev(1), counts((size_t)((p + 1023) / 1024 + 1));
@@ -495,9 +600,35 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                     q.thresh = (float)((double)alpha_f * q.pen_d);                 // enet(): Scalar thresh = alpha * penalty(double)
                     q.denom = (float)(1.0 + q.pen_d * (1.0 - (double)alpha_f));
                     wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, frho, gamma, 0, n, tmp.p); KERNEL_CHECK();
-                    gemv_t<float>(s, X, n, p, ldx, tmp.p, vec.p);
-                    wide_prox_all_kernel<<<(unsigned)((p + WT - 1) / WT), WT, 0, s>>>(vec.p, x.p, p, gamma, q); KERNEL_CHECK();
-                    compact(nullptr, (int)p, supp[cur_supp].p);
+                    if (screen) {
+                        // threshold on |X_j' tmp| below which prox(-vec_j / gamma) = 0: gamma * pen (lasso) / gamma * thresh (enet)
+                        const double thr = (double)gamma * (q.enet ? (double)q.thresh : q.pen_d);
+                        const float thr_safe = (float)(thr * (1.0 - 1e-6));
+                        wide_norm2_kernel<<<1, 1024, 0, s>>>(tmp.p, n, tmpnorm.p); KERNEL_CHECK();
+                        wide_screen_kernel<<<(unsigned)std::min<i64>((p + 7) / 8, (i64)sm_count() * 16), WT, 0, s>>>(
+                            Xh.p, ldh, n, p, tmp.p, x.p, colnorm.p, tmpnorm.p, screen_kx, screen_kn, thr_safe, vec.p);
+                        KERNEL_CHECK();
+                        // candidates = marked columns (sorted); their count comes to the host (one small read per regular step)
+                        {
+                            const int nb = (int)((p + 1023) / 1024);
+                            compact_count_kernel<<<nb, 1024, 0, s>>>(nullptr, vec.p, (int)p, counts.p); KERNEL_CHECK();
+                            compact_scan_kernel<<<1, 1024, 0, s>>>(counts.p, nb, nnz_dev.p); KERNEL_CHECK();
+                            compact_scatter_kernel<<<nb, 1024, 0, s>>>(nullptr, vec.p, (int)p, counts.p, cand.p); KERNEL_CHECK();
+                        }
+                        int ncand = 0;
+                        CUDA_CHECK(cudaMemcpyAsync(&ncand, nnz_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                        CUDA_CHECK(cudaStreamSynchronize(s));
+                        screened_steps += 1; screened_cand += ncand; last_ncand = ncand;
+                        gemv_t_list<float>(s, X, n, ldx, tmp.p, cand.p, ncand, vec.p);
+                        if (ncand > 0) {
+                            wide_prox_list_kernel<<<(unsigned)((ncand + WT - 1) / WT), WT, 0, s>>>(vec.p, cand.p, ncand, x.p, gamma, q); KERNEL_CHECK();
+                        }
+                        compact(cand.p, ncand, supp[cur_supp].p);
+                    } else {
+                        gemv_t<float>(s, X, n, p, ldx, tmp.p, vec.p);
+                        wide_prox_all_kernel<<<(unsigned)((p + WT - 1) / WT), WT, 0, s>>>(vec.p, x.p, p, gamma, q); KERNEL_CHECK();
+                        compact(nullptr, (int)p, supp[cur_supp].p);
+                    }
                 } else {
                     q.thresh = alpha_f * q.pen_f;                                  // active_set_update(): all Scalar
                     q.denom = (float)(1.0 + (double)q.pen_f * (1.0 - (double)alpha_f));
@@ -530,8 +661,10 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             const double resid_primal = (double)std::sqrt((float)h[1]);
             sAx2 = h[2]; sz2 = h[3]; sy2 = h[4];
             nnz = (int)h[5];                                               // exact support size after this iteration's x step
-            work_bytes += 4.0 * (double)n * (step_kind == 1 ? (double)p : step_kind == 2 ? (double)nnz_before : 0.0)
-                        + 4.0 * (double)n * (double)nnz + 48.0 * (double)n;
+            // (a screened regular step reads the fp16 copy of all columns and the float32 data of its candidates)
+            const double xbytes = step_kind == 1 ? (screen ? 2.0 * (double)ldh * (double)p + 4.0 * (double)n * (double)last_ncand : 4.0 * (double)n * (double)p)
+                                : step_kind == 2 ? 4.0 * (double)n * (double)nnz_before : 0.0;
+            work_bytes += xbytes + 4.0 * (double)n * (double)nnz + 48.0 * (double)n;
             if (step_kind == 1) work_regular += 1; else if (step_kind == 2) work_active += 1;
             if (tracing && i < tr.cap) {
                 double* row = tr.buf + 5 * (size_t)i;
@@ -554,7 +687,8 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
     T.iterate = tm.stop();
-    g_last_work[0] = work_bytes; g_last_work[1] = work_regular; g_last_work[2] = work_active; g_last_work[3] = 0;
+    g_last_work[0] = work_bytes; g_last_work[1] = work_regular; g_last_work[2] = work_active;
+    g_last_work[3] = screened_steps > 0 ? screened_cand / screened_steps : 0;      // mean number of columns a screened step evaluates exactly
 
     tm.start();
     out->nlambda = nl;

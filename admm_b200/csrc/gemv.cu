@@ -112,6 +112,32 @@ __global__ void __launch_bounds__(256) gemv_t_seg_finish_kernel(const T* __restr
     out[j] = s;
 }
 
+// the listed columns only: out[list[k]] = A(:, list[k])' v, one warp per entry, with the SAME summation order as
+// gemv_t_warp_kernel (bit-identical values; the wide solver's screened regular step relies on it)
+template <class T>
+__global__ void __launch_bounds__(256) gemv_t_list_kernel(const T* __restrict__ A, i64 m, i64 lda, const T* __restrict__ v,
+                                                          const int* __restrict__ list, int count, T* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
+    for (int k = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); k < count; k += nwarps) {
+        const i64 j = list[k];
+        T s = strided_dot(A + j * lda, v, m, lane, 32);
+        s = warp_sum(s);
+        if (lane == 0) out[j] = s;
+    }
+}
+bool gemv_t_uses_warp_kernel(i64 m) { return m < 32768; }
+template <class T>
+void gemv_t_list(cudaStream_t s, const T* A, i64 m, i64 lda, const T* v, const int* list, int count, T* out)
+{
+    if (count <= 0) return;
+    const i64 blocks = std::min<i64>(((i64)count + 7) / 8, (i64)sm_count() * 8);
+    gemv_t_list_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(A, m, lda, v, list, count, out);
+    KERNEL_CHECK();
+}
+template void gemv_t_list<float>(cudaStream_t, const float*, i64, i64, const float*, const int*, int, float*);
+
 template <class T>
 void gemv_t(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T* out)
 {

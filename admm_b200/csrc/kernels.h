@@ -72,6 +72,9 @@ bool gram_f16_overflowed(cudaStream_t s);
 // ---- gemv.cu -----------------------------------------------------------------------------
 // out[j] = sum_i A(i,j) v[i]   (A m x ncol column-major, lda)  -- one dot product per column
 template <class T> void gemv_t(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T* out);
+// out[list[k]] = A(:, list[k])' v for k < count, bit-identical to gemv_t's value when gemv_t_uses_warp_kernel(m)
+bool gemv_t_uses_warp_kernel(i64 m);
+template <class T> void gemv_t_list(cudaStream_t s, const T* A, i64 m, i64 lda, const T* v, const int* list, int count, T* out);
 // out[i] = sum_j A(i,j) v[j]   -- row-parallel; `work` must hold gemv_n_work(m, ncol) entries
 template <class T> void gemv_n(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T* out, T* work);
 size_t gemv_n_work(i64 m, i64 ncol);

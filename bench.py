@@ -791,10 +791,13 @@ def run_wide(args):
     line.update({"path_wall_s": dev_s / steps, "niter_path": nit, "phase_s": T, "us_per_iteration": T["iterate"] / max(nit, 1) * 1e6,
                  "regular_steps": int(work[1]), "active_set_steps": int(work[2]), "gamma": f.info["eig"], "rho_final": f.info["rho"],
                  "support_last_lambda": int(f.beta[:, -1].nnz) - 1,
-                 "roofline": {"kernel": "wide iteration kernels (gemv_t over X on regular steps, wide_active / wide_ax column gathers otherwise)",
+                 "roofline": {"kernel": "wide iteration kernels (wide_screen over the fp16 copy + gemv_t_list on regular steps, wide_active / wide_ax column gathers otherwise)",
                               "bound": "hbm", "achieved": achieved, "peak": env.hbm_peak, "unit": "GB/s", "frac": achieved / env.hbm_peak,
                               "traffic": None, "algorithmic_bytes": float(work[0]),
-                              "note": "sum over iterations of 4 n p (regular) or 4 n nnz_k (active set) + 4 n nnz_{k+1} + 48 n, / iterate seconds",
+                              "note": "sum over iterations of [2 n p (fp16 screen) + 4 n candidates] (screened regular step; 4 n p unscreened) or "
+                                      "4 n nnz_k (active set), + 4 n nnz_{k+1} + 48 n, / iterate seconds",
+                              "screened": os.environ.get("B200ADMM_WIDE_SCREEN", "1") != "0",
+                              "mean_columns_evaluated_exactly_per_regular_step": float(work[3]),
                               "peak_source": env.peak_src},
                  "clocks": clocks, "gpu_launches": int(launches), "device": env.info["name"]})
     ok = True

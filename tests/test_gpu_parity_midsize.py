@@ -206,6 +206,30 @@ def test_wide_n2000_p20000(A, O):
     report("wide n=2000 p=20000 30 lambda", dense(f.beta), o["beta"], f.niter, o["niter"], 3e-4, 3e-4)
 
 
+@pytest.mark.parametrize("n,p,model,alpha", [(2000, 20000, "lasso", 1.0), (301, 6000, "lasso", 1.0), (640, 9000, "enet", 0.4)])
+def test_wide_screened_regular_steps_are_bit_identical(A, monkeypatch, n, p, model, alpha):
+    """The regular steps of the wide solver screen the p columns through an fp16 copy with a rigorous error bound and
+    evaluate only the candidates from the float32 data (admm_wide.cu: wide_screen_kernel): every coefficient, iteration
+    count and the trace must equal the unscreened run (B200ADMM_WIDE_SCREEN=0) bit for bit.  n = 301: padded fp16 columns."""
+    from admm_b200 import _capi as K
+    rng = np.random.default_rng(n + p)
+    x = np.asfortranarray(rng.normal(0.2, 2.0, size=(n, p)).astype(np.float32))
+    b = np.zeros(p)
+    b[rng.choice(p, 15, replace=False)] = rng.uniform(0.5, 1.5, size=15)
+    y = (1.0 + x @ b + rng.normal(size=n)).astype(np.float32)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200ADMM_WIDE_SCREEN", mode)
+        with K.trace(which=5, cap=400) as tr:
+            m = A.admm_lasso(x, y).penalty(nlambda=10) if model == "lasso" else A.admm_enet(x, y).penalty(nlambda=10, alpha=alpha)
+            f = m.fit()
+        out[mode] = (dense(f.beta), f.niter.copy(), tr.rows.copy())
+    assert np.array_equal(out["1"][1], out["0"][1]), (out["1"][1], out["0"][1])
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.array_equal(out["1"][2], out["0"][2])
+    assert int(out["1"][1].max()) > 16                     # several regular steps (iterations 0, 3, 15, ...) per lambda
+
+
 def test_lad_n20000_p300(A, O):
     rng = np.random.default_rng(8)
     n, p = 20_000, 300
