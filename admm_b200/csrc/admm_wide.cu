@@ -158,22 +158,31 @@ __global__ void __launch_bounds__(WT) wide_screen_kernel(const __half* __restric
     const i64 nwarps = (i64)gridDim.x * (WT >> 5);
     const float tn = *tmpnorm;
     const i64 nv = ldh / 8;                                  // 16-byte groups of 8 halves per column
+    (void)n;
     for (i64 j = (i64)blockIdx.x * (WT >> 5) + (threadIdx.x >> 5); j < p; j += nwarps) {
         if (x[j] != 0.f) { if (lane == 0) mark[j] = 1.f; continue; }
         const uint4* col = reinterpret_cast<const uint4*>(Xh + j * ldh);
         float s0 = 0.f, s1 = 0.f;
-        for (i64 g = lane; g < nv; g += 32) {
-            uint4 h;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(col + g));
-            const i64 i0 = g * 8;
-            float t[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) t[e] = i0 + e < n ? tmp[i0 + e] : 0.f;
+        // eight halves per 16-byte load against two float4 of tmp (tmp is padded with zeros up to ldh by the caller);
+        // four loads in flight per lane
+        auto acc8 = [&](const uint4& h, i64 g) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(tmp) + 2 * g), t1 = __ldg(reinterpret_cast<const float4*>(tmp) + 2 * g + 1);
             const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
             const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
-            s0 = fmaf(a.x, t[0], s0); s1 = fmaf(a.y, t[1], s1); s0 = fmaf(b.x, t[2], s0); s1 = fmaf(b.y, t[3], s1);
-            s0 = fmaf(c.x, t[4], s0); s1 = fmaf(c.y, t[5], s1); s0 = fmaf(d.x, t[6], s0); s1 = fmaf(d.y, t[7], s1);
+            s0 = fmaf(a.x, t0.x, s0); s1 = fmaf(a.y, t0.y, s1); s0 = fmaf(b.x, t0.z, s0); s1 = fmaf(b.y, t0.w, s1);
+            s0 = fmaf(c.x, t1.x, s0); s1 = fmaf(c.y, t1.y, s1); s0 = fmaf(d.x, t1.z, s0); s1 = fmaf(d.y, t1.w, s1);
+        };
+        auto ldh4 = [&](i64 g) {
+            uint4 h;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(col + g));
+            return h;
+        };
+        i64 g = lane;
+        for (; g + 96 < nv; g += 128) {
+            const uint4 h0 = ldh4(g), h1 = ldh4(g + 32), h2 = ldh4(g + 64), h3 = ldh4(g + 96);
+            acc8(h0, g); acc8(h1, g + 32); acc8(h2, g + 64); acc8(h3, g + 96);
         }
+        for (; g < nv; g += 32) acc8(ldh4(g), g);
         const float sj = warp_sum(s0 + s1);
         if (lane == 0) {
             const float e = (kx * colnorm[j] + kn) * tn;
@@ -536,7 +545,8 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     int last_ncand = 0;
 
     // ---- state ---------------------------------------------------------------------------------------
-    DevBuf<float> x(p), Ax(n), z(n), y(n), tmp(n);
+    DevBuf<float> x(p), Ax(n), z(n), y(n), tmp(ldh);            // (tmp: zero-padded to the fp16 columns' length for the screen)
+    tmp.zero(s);
     DevBuf<int> supp[2], nnz_dev(1), counts((size_t)((p + 1023) / 1024 + 1));
     supp[0].alloc(p); supp[1].alloc(p);
     x.zero(s); Ax.zero(s); z.zero(s); y.zero(s); nnz_dev.zero(s);
