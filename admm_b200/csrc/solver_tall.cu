@@ -143,10 +143,18 @@ std::vector<i64> host_panel_schedule(i64 p, i64 pw)
 // independent: a few host threads rescale them (same arithmetic and order per lambda as recover_sparse) and count their
 // non-zeros, then fill their slices of the dgCMatrix arrays (5 ms -> ~1 ms at p = 1e4 x 100 lambdas, which is 5 % of an
 // 8-GPU fit).
+void finish_lasso_path_inplace(float* c_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
+                               const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out);
 void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
                        const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out)
 {
-    std::vector<float> c(z_all);                         // rescaled in place
+    std::vector<float> c(z_all);
+    finish_lasso_path_inplace(c.data(), nl, p, flag, meanX, scaleX, meanY, scaleY, out);
+}
+// (c_all: nl x p standardised solutions, rescaled in place)
+void finish_lasso_path_inplace(float* c_all, int nl, i64 p, int flag, const std::vector<float>& meanX,
+                               const std::vector<float>& scaleX, float meanY, float scaleY, b200admm_path* out)
+{
     std::vector<float> beta0(nl, 0.f);
     std::vector<size_t> cnt(nl, 0);
     const int nthreads = (int)std::max<i64>(1, std::min<i64>(8, std::min<i64>(nl, ((i64)nl * p) >> 16)));
@@ -158,7 +166,7 @@ void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag,
         for (auto& x : th) x.join();
     };
     for_lambdas([&](int k) {
-        float* ck = c.data() + (size_t)k * p;
+        float* ck = c_all + (size_t)k * p;
         float s = 0.f;
         size_t nz = 0;
         for (i64 j = 0; j < p; j++) {
@@ -180,7 +188,7 @@ void finish_lasso_path(const std::vector<float>& z_all, int nl, i64 p, int flag,
     out->val = (double*)malloc(sizeof(double) * std::max<size_t>(nnz, 1));
     if (!out->rowidx || !out->val) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
     for_lambdas([&](int k) {
-        const float* ck = c.data() + (size_t)k * p;
+        const float* ck = c_all + (size_t)k * p;
         size_t pos = (size_t)out->colptr[k];
         out->rowidx[pos] = 0; out->val[pos] = (double)beta0[k]; pos++;
         for (i64 j = 0; j < p; j++)
@@ -519,6 +527,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     if (!pb && !(tri_env && !strcmp(tri_env, "0"))) {
         const size_t nf = tall_tri_part_floats((int)p);
         if (nf) { tri_part.alloc(nf); a.tri_part = tri_part.p; }
+        if (const char* sw = getenv("B200ADMM_TRI_SWEEP")) a.tri_sweep = atoi(sw);
     }
     tm.start();
     launch_tall_path(s, a);
@@ -526,11 +535,21 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
 
     // ---- results --------------------------------------------------------------------------------
     tm.start();
-    std::vector<float> z_all((size_t)nl * (size_t)p);
+    // (pinned staging buffer kept between calls: the 4 MB of solutions come back at PCIe speed instead of through the
+    // driver's pageable path, and are rescaled where they land)
+    static float* z_host = nullptr;
+    static size_t z_host_floats = 0;
+    const size_t z_floats = (size_t)nl * (size_t)p;
+    if (z_floats > z_host_floats) {
+        if (z_host) cudaFreeHost(z_host);
+        z_host = nullptr; z_host_floats = 0;
+        CUDA_CHECK(cudaHostAlloc((void**)&z_host, z_floats * sizeof(float), cudaHostAllocDefault));
+        z_host_floats = z_floats;
+    }
     out->niter = (int*)malloc(sizeof(int) * nl);
     out->lambda = (double*)malloc(sizeof(double) * nl);
     if (!out->niter || !out->lambda) throw CodeError(B200ADMM_ENOMEM, "out of host memory");
-    CUDA_CHECK(cudaMemcpyAsync(z_all.data(), z_out_p, z_all.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(z_host, z_out_p, z_floats * sizeof(float), cudaMemcpyDeviceToHost, s));
     int aborted = 0;
     if (pb) CUDA_CHECK(cudaMemcpyAsync(&aborted, abort_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(out->niter, niter_dev.p, nl * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -554,7 +573,7 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     if (aborted) throw CodeError(B200ADMM_ENCCL, "sharded lambda path: a peer rank did not reach the iteration barrier in time");
     for (int k = 0; k < nl; k++) out->lambda[k] = lam[k];
     out->nlambda = nl;
-    finish_lasso_path(z_all, nl, p, flag, st.meanX, st.scaleX, st.meanY, st.scaleY, out);
+    finish_lasso_path_inplace(z_host, nl, p, flag, st.meanX, st.scaleX, st.meanY, st.scaleY, out);
     T.finish = tm.stop();
     T.total = wall_now() - t_begin;
     out->rho = rho; out->eig = ev; out->lambda0 = lambda0; out->t = T;
