@@ -435,7 +435,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_kernel(TallPathArgs a
 // because neither kernel is HBM-bound at the clock the iteration phase runs at in a whole fit (~1.4 GHz right after the
 // power-capped Gram): an SM takes in ~34 B / cycle from L2 (full-row kernel: 400 MB in 84.5 k cycles = 32 B / cycle / SM),
 // and this sweep spends two FMAs per element plus the row-sum butterflies.  Two ring-buffered variants of phase [A]
-// (per-thread cp.async, TMA bulk copies with full / empty mbarriers; git history) were slower: 63 and 75 us.
+// (per-thread cp.async, TMA bulk copies with full / empty mbarriers; git history) were slower: 63 and 75 us; so was a
+// warp-tile sweep (warp = 128-column tiles, chunks of eight rows, column sums in registers): 86.8 k cycles for phase [A]
+// against 65.0 k (profiles/r2t_*).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TRI_ROWS = 8;                 // rows per group (loads in flight per thread)
 constexpr int TRI_STRIPE = TP_THREADS * 4;  // columns per stripe
@@ -533,80 +535,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
             const double eps_dual = (double)sqrtf((float)sy2) * a.eps_rel + sqrt_p * a.eps_abs;
 
             // ---- [A] lower-triangle sweep of the own rows --------------------------------------------
-            const bool rev = a.snake && (git & 1u);
-            if (a.tri_sweep == 1) {
-                // Warp-tile sweep: warp w owns the 128-column tiles w, w + 16, ... (lane = four columns) and walks down the
-                // own rows in chunks of eight: the transposed contributions of a tile stay in four registers for the whole
-                // walk and are stored once, the row sums of a chunk are reduced by one butterfly and added to the warp's
-                // private row-sum slots.  Against the thread-column sweep below: no shared-memory read-modify-write per
-                // step, every lane busy except on the tile that holds the diagonal.
-                for (int r = lane; r < 2 * vpad; r += 32) s_dot[warp * 2 * vpad + r] = 0.f;
-                __syncwarp();
-                const int maxrow = nB > 0 ? b1 - 1 : t1 - 1;
-                const int nct = nown > 0 ? maxrow / 128 + 1 : 0, nct_all = (ld + 127) / 128;
-                const int nch = (nown + TRI_ROWS - 1) / TRI_ROWS;
-                for (int cc = warp; cc < nct_all; cc += TP_WARPS) {
-                    const int ct = cc < nct ? (rev ? nct - 1 - cc : cc) : cc;
-                    const int c0 = 128 * ct, j0 = c0 + 4 * lane;
-                    const bool lane_in = j0 < ld;
-                    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (cc < nct) {
-                        const float4 rj = lane_in ? reinterpret_cast<const float4*>(rhs)[32 * ct + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        // rows of the own list (ascending) that reach this tile: i >= c0
-                        const int rf = c0 <= t0 ? 0 : (c0 < t1 ? c0 - t0 : (c0 <= b0 ? nT : min(nown, nT + (c0 - b0))));
-                        const int ch_first = rf / TRI_ROWS;
-                        for (int cq = ch_first; cq < nch; cq++) {
-                            const int ch = rev ? (nch - 1 - (cq - ch_first)) : cq;
-                            float d[TRI_ROWS], ri[TRI_ROWS];
-                            int irow[TRI_ROWS];
-                            int imin = 0x7fffffff;
-#pragma unroll
-                            for (int r = 0; r < TRI_ROWS; r++) {
-                                const int rr = ch * TRI_ROWS + r;
-                                const int i = rr < nown ? own_row(rr) : -1;
-                                irow[r] = i >= c0 ? i : -1;
-                                imin = min(imin, irow[r]);
-                                ri[r] = irow[r] >= 0 ? rhs[irow[r]] : 0.f;
-                                d[r] = 0.f;
-                            }
-                            float4 q[TRI_ROWS];
-#pragma unroll
-                            for (int r = 0; r < TRI_ROWS; r++)
-                                q[r] = (lane_in && irow[r] >= j0) ? ld_stream_f4(reinterpret_cast<const float4*>(a.Kinv + (size_t)irow[r] * ld + j0))
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (imin >= c0 + 128) {
-                                // all eight rows lie below this tile's columns
-#pragma unroll
-                                for (int r = 0; r < TRI_ROWS; r++) {
-                                    d[r] = fmaf(q[r].x, rj.x, d[r]); d[r] = fmaf(q[r].y, rj.y, d[r]);
-                                    d[r] = fmaf(q[r].z, rj.z, d[r]); d[r] = fmaf(q[r].w, rj.w, d[r]);
-                                    av.x = fmaf(q[r].x, ri[r], av.x); av.y = fmaf(q[r].y, ri[r], av.y);
-                                    av.z = fmaf(q[r].z, ri[r], av.z); av.w = fmaf(q[r].w, ri[r], av.w);
-                                }
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < TRI_ROWS; r++) {
-                                    const int i = irow[r];                      // -1: not a row of this tile (loaded as zeros)
-                                    const float qx = j0 <= i ? q[r].x : 0.f, qy = j0 + 1 <= i ? q[r].y : 0.f;
-                                    const float qz = j0 + 2 <= i ? q[r].z : 0.f, qw = j0 + 3 <= i ? q[r].w : 0.f;
-                                    d[r] = fmaf(qx, rj.x, d[r]); d[r] = fmaf(qy, rj.y, d[r]);
-                                    d[r] = fmaf(qz, rj.z, d[r]); d[r] = fmaf(qw, rj.w, d[r]);
-                                    av.x = fmaf(j0 < i ? qx : 0.f, ri[r], av.x); av.y = fmaf(j0 + 1 < i ? qy : 0.f, ri[r], av.y);
-                                    av.z = fmaf(j0 + 2 < i ? qz : 0.f, ri[r], av.z); av.w = fmaf(j0 + 3 < i ? qw : 0.f, ri[r], av.w);
-                                }
-                            }
-                            const float tot = butterfly8(d, lane);
-                            if ((lane & 3) == 0) {
-                                const int rr = ch * TRI_ROWS + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                                if (rr < nown) s_dot[warp * 2 * vpad + (rr < nT ? rr : vpad + (rr - nT))] += tot;
-                            }
-                        }
-                    }
-                    if (lane_in) reinterpret_cast<float4*>(acc)[32 * ct + lane] = av;
-                }
-                __syncthreads();
-            } else {
             for (int v = tid; v < nvec; v += TP_THREADS) reinterpret_cast<float4*>(acc)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool rev = a.snake && (git & 1u);
             const int ngT = (nT + TRI_ROWS - 1) / TRI_ROWS, ngB = (nB + TRI_ROWS - 1) / TRI_ROWS;
             for (int gg = 0; gg < ngT + ngB; gg++) {
                 const int g = rev ? (ngT + ngB - 1 - gg) : gg;
@@ -658,8 +588,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tall_path_tri_kernel(TallPathAr
                     s_dot[warp * 2 * vpad + (bottom ? vpad : 0) + g0 + r] = tot;
                 }
             }
-            }
-            // the CTA's partial column sums -> global
+            // the CTA's partial column sums -> global (every thread stores the slots it owns)
             {
                 float4* dst = reinterpret_cast<float4*>(part + (size_t)cta * ld);
                 for (int v = tid; v < nvec; v += TP_THREADS) __stcg(dst + v, reinterpret_cast<const float4*>(acc)[v]);

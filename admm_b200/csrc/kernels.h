@@ -145,7 +145,6 @@ struct TallPathArgs {
     // single GPU: workspace of tall_tri_part_floats(p) floats selects the kernel that reads one triangle of Kinv per
     // iteration (nullptr: the full-row kernel)
     float* tri_part = nullptr;
-    int tri_sweep = 1;      // phase [A] of the one-triangle kernel: 1 warp-tile sweep, 0 thread-column sweep (B200ADMM_TRI_SWEEP)
 };
 size_t tall_state_floats(int p);
 size_t tall_tri_part_floats(int p);   // 0: p too large for the one-triangle kernel

@@ -527,7 +527,6 @@ void solve_lasso_like(const LassoRequest& rq, b200admm_path* out)
     if (!pb && !(tri_env && !strcmp(tri_env, "0"))) {
         const size_t nf = tall_tri_part_floats((int)p);
         if (nf) { tri_part.alloc(nf); a.tri_part = tri_part.p; }
-        if (const char* sw = getenv("B200ADMM_TRI_SWEEP")) a.tri_sweep = atoi(sw);
     }
     tm.start();
     launch_tall_path(s, a);

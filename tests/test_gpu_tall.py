@@ -106,7 +106,9 @@ def test_path_matches_oracle(A, O, n, p, model, alpha):
     for k in range(nl):
         assert_beta_close(bg[:, k], bc[:, k], tol=tol, band=tol)
     ng, nc = f.niter.astype(int), o["niter"].astype(int)
-    assert abs(ng.sum() - nc.sum()) <= max(3, 0.03 * nc.sum()), (ng, nc)
+    # (5 % on the total: at the small-lambda end the oracle's own counts oscillate -- 37, 4, 49, 4, 42, 4, 41 measured for
+    # enet n = 3000, p = 256 -- and shift with the summation order of the host BLAS, i.e. with the box's core count)
+    assert abs(ng.sum() - nc.sum()) <= max(3, 0.05 * nc.sum()), (ng, nc)
     # Early in the path the counts are identical.  At the small-lambda end the warm-started
     # iterate sits at the float32 noise floor of the stopping rule (eps 1e-5 relative on float
     # vectors), so a last-ulp difference in a norm moves single lambdas by a few iterations in
