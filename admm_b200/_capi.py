@@ -23,7 +23,7 @@ EXPORTS = [
     "b200admm_last_error", "b200admm_version", "b200admm_launch_count", "b200admm_last_gram_seconds", "b200admm_last_work", "b200admm_stream", "b200admm_release_cache", "b200admm_device_info", "b200admm_set_trace",
     "b200admm_synth_f32",
     "b200admm_k_standardize_f32", "b200admm_k_gram_f32", "b200admm_k_gemv_t_f32",
-    "b200admm_k_gram_plan", "b200admm_k_panel_schedule", "b200admm_k_lambda_grid", "b200admm_k_coarse_eig_f32", "b200admm_k_gemm_tn_f32", "b200admm_k_gemm_f64",
+    "b200admm_k_gram_plan", "b200admm_k_panel_schedule", "b200admm_k_tri_plan", "b200admm_k_lambda_grid", "b200admm_k_coarse_eig_f32", "b200admm_k_gemm_tn_f32", "b200admm_k_gemm_f64",
     "b200admm_k_chol_f32", "b200admm_k_spd_inverse_f32", "b200admm_k_fused_zu_f32",
 ]
 
@@ -108,6 +108,7 @@ def lib():
         L.b200admm_k_gram_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         L.b200admm_k_gram_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200admm_k_panel_schedule.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        L.b200admm_k_tri_plan.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
         L.b200admm_k_lambda_grid.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.b200admm_k_gemv_t_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.b200admm_k_coarse_eig_f32.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p]

@@ -657,6 +657,14 @@ int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int
     } catch (...) { return -1; }
 }
 
+int b200admm_k_tri_plan(int p, int sms, int* rows, int cap, long long* smem_bytes)
+{
+    try {
+        if (p < 1 || sms < 1) return -1;
+        return tall_tri_plan(p, sms, rows, cap, smem_bytes);
+    } catch (...) { return -1; }
+}
+
 int b200admm_k_lambda_grid(double lmax, double lmin_ratio, int nlambda, double* out)
 {
     return fenced([&] {

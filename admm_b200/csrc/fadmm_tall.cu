@@ -823,6 +823,24 @@ static int tri_grid(int p, int sms, int* vrows_per_cta, size_t* smem_bytes)
     *smem_bytes = sizeof(float) * (2 * (size_t)ld + (size_t)(TP_WARPS + 1) * 2 * vpad);
     return (*smem_bytes <= 200 * 1024) ? G : 0;
 }
+// host-only replay of the one-triangle kernel's row assignment (b200admm_k_tri_plan): rows[4 c .. 4 c + 3] = t0, t1, b0, b1 of CTA c
+int tall_tri_plan(int p, int sms, int* rows, int cap, long long* smem_bytes)
+{
+    int vr; size_t sm;
+    const int G = tri_grid(p, sms, &vr, &sm);
+    if (smem_bytes) *smem_bytes = (long long)sm;
+    if (G <= 0) return 0;
+    if (rows) {
+        if (cap < G) return -1;
+        const int V = (p + 1) / 2;
+        for (int c = 0; c < G; c++) {
+            const int t0 = std::min(V, c * vr), t1 = std::min(V, t0 + vr);
+            rows[4 * c] = t0; rows[4 * c + 1] = t1; rows[4 * c + 2] = std::max(p - t1, t1); rows[4 * c + 3] = p - t0;
+        }
+    }
+    return G;
+}
+
 size_t tall_tri_part_floats(int p)
 {
     int vr; size_t sm;

@@ -148,6 +148,7 @@ struct TallPathArgs {
 };
 size_t tall_state_floats(int p);
 size_t tall_tri_part_floats(int p);   // 0: p too large for the one-triangle kernel
+int tall_tri_plan(int p, int sms, int* rows, int cap, long long* smem_bytes);   // host only: grid size (0: not taken, -1: cap)
 // returns the grid size used
 int launch_tall_path(cudaStream_t s, const TallPathArgs& a);
 

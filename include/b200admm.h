@@ -204,6 +204,11 @@ int b200admm_k_gram_f32(const void* x, int64_t n, int64_t p, void* g /* p x p, f
  * (returns the number of panels, begin[0 .. npanels] their first columns; -1 on bad arguments). */
 int b200admm_k_gram_plan(int ntiles, int npairs, int nk, int* cover, long long* per_pair, int* nslices, int* split_tiles);
 int b200admm_k_panel_schedule(int64_t p, int64_t panel_cols, int64_t* begin, int cap);
+/* Host-only replay of the row assignment of the single-GPU iteration kernel that reads one triangle of K^-1
+ * (fadmm_tall.cu: tall_path_tri_kernel): CTA c owns the rows [rows[4c], rows[4c+1]) and [rows[4c+2], rows[4c+3]) of a p x p
+ * matrix on a device with `sms` SMs.  Returns the grid size, 0 when the shape does not take that kernel (shared memory),
+ * -1 on bad arguments / cap too small; smem_bytes (optional) = dynamic shared memory of the launch. */
+int b200admm_k_tri_plan(int p, int sms, int* rows, int cap, long long* smem_bytes);
 /* Host-only: the default lambda sequence of admm_lasso / admm_enet (src/Lasso.cpp:78-89,
  * `lambda.setLinSpaced(nlambda, log(lmax), log(lmin)).exp()` with Eigen's LinSpaced semantics: a single
  * value is the HIGH end, i.e. nlambda = 1 fits at lmin_ratio * lmax).  out: nlambda doubles. */

@@ -73,6 +73,9 @@ def test_front_end_defaults_and_validation():
     assert (m.nlambda, m.lambda_min_ratio, m.nthread, m.maxit, m.eps_abs, m.eps_rel, m.rho) == \
            (100, 1e-4, 1, 10000, 1e-5, 1e-5, -1.0)
     assert A.admm_lasso(np.zeros((5, 12)), np.zeros(5)).lambda_min_ratio == 0.01
+    # a default goes to the library as 0 (resolved there from the GLOBAL row count of a row-sharded run), a user's value as is
+    assert m._lmr_arg() == 0.0 and m.penalty(nlambda=5)._lmr_arg() == 0.0
+    assert m.penalty(lambda_min_ratio=0.5)._lmr_arg() == 0.5
     assert m.penalty([0.1, 0.5, 0.2]).lambda_.tolist() == [0.5, 0.2, 0.1]      # sorted decreasingly
     assert m.penalty() is m and m.opts() is m and m.parallel(2) is m
     for bad in (lambda: m.penalty([-1.0]), lambda: m.penalty(nlambda=0), lambda: m.penalty(lambda_min_ratio=1.0),

@@ -122,3 +122,36 @@ def test_oracle_single_lambda_default_is_the_low_end():
     two = O.lasso_path(x, y, nlambda=2)
     assert np.isclose(one["lambda_"][0], two["lambda_"][1], rtol=1e-14)
     assert np.isclose(one["lambda_"][0], 1e-4 * two["lambda_"][0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("p", [3, 8, 20, 37, 256, 1001, 1100, 2310, 4100, 10000, 10001, 20000])
+@pytest.mark.parametrize("sms", [148, 132, 16])
+def test_one_triangle_row_assignment_covers_every_row_once_and_balances_the_bytes(L, p, sms):
+    """tall_path_tri_kernel reads row i of the symmetric K^-1 up to the diagonal (i + 1 entries); CTA c owns the folded
+    rows [t0, t1) and [p - t1, p - t0): every row exactly once, and -- a folded pair has p + 1 entries -- the same number
+    of entries per CTA up to one pair (the last CTA may own fewer)."""
+    rows = np.zeros(4 * 1024, dtype=np.int32)
+    smem = C.c_longlong(0)
+    G = L.b200admm_k_tri_plan(p, sms, rows.ctypes.data, 1024, C.byref(smem))
+    if G == 0:                          # few SMs: the per-warp row-sum slots of 2 x 625 rows do not fit next to 2 p floats
+        assert sms == 16 and p == 20000
+        return
+    assert 0 < G <= sms and smem.value <= 227 * 1024
+    seen = np.zeros(p, dtype=np.int32)
+    work = []
+    for c in range(G):
+        t0, t1, b0, b1 = (int(v) for v in rows[4 * c:4 * c + 4])
+        assert 0 <= t0 <= t1 <= b0 <= b1 <= p
+        seen[t0:t1] += 1
+        seen[b0:b1] += 1
+        work.append(sum(i + 1 for i in range(t0, t1)) + sum(i + 1 for i in range(b0, b1)))
+    assert (seen == 1).all()
+    assert sum(work) == p * (p + 1) // 2
+    full = work[:-1] if G > 1 else work
+    assert max(full) - min(full) <= p + 1                       # all but the last CTA: within one folded pair of each other
+    assert work[-1] <= max(full)
+
+
+def test_one_triangle_kernel_is_declined_when_two_p_vectors_do_not_fit_shared_memory(L):
+    assert L.b200admm_k_tri_plan(60000, 148, None, 0, None) == 0
+    assert L.b200admm_k_tri_plan(10000, 148, None, 0, None) == 148
