@@ -44,6 +44,21 @@ struct WideProx {
     float thresh, denom;
 };
 
+// device-side loop control of runs of active-set steps (see wide_control_kernel)
+struct WideCtl {
+    double rho, sAx2, sz2, sy2;                          // rho and the squared norms of the current Ax, z, y
+    double eps_primal, resid_primal, eps_dual, resid_dual;   // of the last executed iteration
+    double work_bytes;                                   // algorithmic bytes of the executed iterations
+    float frho, pen_f, thresh, denom, den;               // parameters of the next active-set iteration
+    int stop, iters, nnz;                                // converged flag, iterations executed, support size
+};
+struct WideCtlConst {                                    // per-lambda constants of the control kernel
+    double eps_abs, eps_rel, sqrt_n, sqrt_p, lambda;
+    float gamma, sqrt_sprad, alpha_f;
+    int enet, i_start;
+    long long n;
+};
+
 __device__ __forceinline__ float prox_regular(float v, const WideProx& q)
 {
     if (!q.enet) {
@@ -69,8 +84,10 @@ __device__ __forceinline__ float prox_active(float v, const WideProx& q)
 
 // tmp = (Ax + z) + y / frho      [optionally / gamma]
 __global__ void __launch_bounds__(WT) wide_tmp_kernel(const float* __restrict__ Ax, const float* __restrict__ z, const float* __restrict__ y,
-                                                      float frho, float gamma, int divide, i64 n, float* __restrict__ tmp)
+                                                      float frho, float gamma, int divide, i64 n, float* __restrict__ tmp,
+                                                      const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl) { if (ctl->stop) return; frho = ctl->frho; }
     const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
     if (i >= n) return;
     float t = (Ax[i] + z[i]) + y[i] / frho;
@@ -89,8 +106,13 @@ __global__ void __launch_bounds__(WT) wide_prox_all_kernel(const float* __restri
 
 // active step: one warp per support column
 __global__ void __launch_bounds__(WT) wide_active_kernel(const float* __restrict__ X, i64 ldx, i64 n, const float* __restrict__ tmp,
-                                                         const int* __restrict__ supp, int nnz, float* __restrict__ x, WideProx q)
+                                                         const int* __restrict__ supp, int nnz, float* __restrict__ x, WideProx q,
+                                                         const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl) {                                           // batched run: support size and prox parameters live on the device
+        if (ctl->stop) return;
+        nnz = ctl->nnz; q.pen_f = ctl->pen_f; q.thresh = ctl->thresh; q.denom = ctl->denom;
+    }
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * WT) >> 5;
     for (int k = (blockIdx.x * WT + threadIdx.x) >> 5; k < nnz; k += warps) {
@@ -201,18 +223,88 @@ __global__ void __launch_bounds__(WT) wide_prox_list_kernel(const float* __restr
     x[j] = prox_regular(v, q);
 }
 
+// ---- device-side loop control for runs of active-set steps ---------------------------------------------------
+// Between two regular steps (iteration counters 4^k - 1) every iteration is an active-set step whose launch shapes are
+// bounded by the support size at the start of the run (the support only shrinks).  Such a run is enqueued as ONE batch
+// without host round trips: the scalars the host loop computes after every iteration -- tolerances from the previous
+// iterate, residuals, the stopping rule, ADMMBase::update_rho (src/ADMMBase.h:192-216) and the prox parameters derived
+// from rho -- are evaluated by wide_control_kernel in the same double / float expressions (IEEE, no contraction on either
+// side), and every kernel of the batch starts by looking at the stop flag.  The host reads the block back once per batch.
+__device__ __forceinline__ void wide_derive_params(WideCtl* c, const WideCtlConst& k)
+{
+    c->frho = (float)c->rho;
+    const double pen_d = k.lambda / (c->rho * (double)k.gamma);
+    c->pen_f = (float)pen_d;
+    c->thresh = k.alpha_f * c->pen_f;                                    // active_set_update(): all Scalar
+    c->denom = (float)(1.0 + (double)c->pen_f * (1.0 - (double)k.alpha_f));
+    c->den = (float)(-1 - c->rho);
+}
+__global__ void wide_ctl_init_kernel(WideCtl* c, WideCtlConst k, const int* __restrict__ nnz_dev)
+{
+    if (threadIdx.x == 0) {
+        c->stop = 0; c->iters = 0; c->work_bytes = 0.0; c->nnz = *nnz_dev;
+        wide_derive_params(c, k);
+    }
+}
+// end of an iteration: sums -> tolerances, residuals, stopping rule, rho balancing, next parameters, trace row
+__global__ void wide_control_kernel(WideCtl* c, WideCtlConst k, const float* __restrict__ psums, int nblocks, const int* __restrict__ nnz_dev,
+                                    double* __restrict__ trace, int trace_cap)
+{
+    __shared__ double h[5];
+    if (c->stop) return;
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q < 5) {
+        double s = 0.0;
+        for (int b = lane; b < nblocks; b += 32) s += (double)psums[(size_t)b * 5 + q];
+        s = warp_sum(s);
+        if (lane == 0) h[q] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int i = k.i_start + c->iters;
+    const double eps_primal = fmax((double)sqrtf((float)c->sAx2), (double)sqrtf((float)c->sz2)) * k.eps_rel + k.sqrt_n * k.eps_abs;
+    const double eps_dual = (double)(k.sqrt_sprad * sqrtf((float)c->sy2)) * k.eps_rel + k.sqrt_p * k.eps_abs;
+    const double rho = c->rho;
+    const double resid_dual = rho * (double)k.sqrt_sprad * (double)sqrtf((float)h[0]);
+    const double resid_primal = (double)sqrtf((float)h[1]);
+    const int nnz_before = c->nnz, nnz = *nnz_dev;
+    c->sAx2 = h[2]; c->sz2 = h[3]; c->sy2 = h[4];
+    c->nnz = nnz;
+    c->work_bytes += 4.0 * (double)k.n * (double)nnz_before + 4.0 * (double)k.n * (double)nnz + 48.0 * (double)k.n;
+    c->eps_primal = eps_primal; c->resid_primal = resid_primal; c->eps_dual = eps_dual; c->resid_dual = resid_dual;
+    if (trace && i < trace_cap) {
+        double* row = trace + 5 * (size_t)i;
+        row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
+    }
+    c->iters += 1;
+    if (resid_primal < eps_primal && resid_dual < eps_dual) { c->stop = 1; return; }
+    if (i > 3) {
+        double r = rho;                                                       // balance_rho
+        if (resid_primal / eps_primal > 10 * resid_dual / eps_dual) r *= 2;
+        else if (resid_dual / eps_dual > 10 * resid_primal / eps_primal) r /= 2;
+        if (resid_primal < eps_primal) r /= 1.2;
+        if (resid_dual < eps_dual) r *= 1.2;
+        c->rho = r;
+    }
+    wide_derive_params(c, k);
+}
+
 // ---- stable compaction of "x[j] != 0" into a sorted index list ---------------------------------
 // src == nullptr: candidates are 0..len-1; otherwise candidates are src[0..len-1] (already sorted)
-__global__ void __launch_bounds__(1024) compact_count_kernel(const int* __restrict__ src, const float* __restrict__ x, int len, int* __restrict__ counts)
+__global__ void __launch_bounds__(1024) compact_count_kernel(const int* __restrict__ src, const float* __restrict__ x, int len, int* __restrict__ counts,
+                                                             const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl) { if (ctl->stop) return; len = ctl->nnz; }   // (blocks beyond the exact length count zero)
     const int i = blockIdx.x * 1024 + threadIdx.x;
     int keep = 0;
     if (i < len) { const int j = src ? src[i] : i; keep = x[j] != 0.f; }
     const int c = __syncthreads_count(keep);
     if (threadIdx.x == 0) counts[blockIdx.x] = c;
 }
-__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ counts, int nb, int* __restrict__ total)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ counts, int nb, int* __restrict__ total,
+                                                            const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl && ctl->stop) return;
     __shared__ int sh[1024];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -236,8 +328,10 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ co
     if (threadIdx.x == 0) *total = carry;
 }
 __global__ void __launch_bounds__(1024) compact_scatter_kernel(const int* __restrict__ src, const float* __restrict__ x, int len,
-                                                               const int* __restrict__ offsets, int* __restrict__ out)
+                                                               const int* __restrict__ offsets, int* __restrict__ out,
+                                                               const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl) { if (ctl->stop) return; len = ctl->nnz; }
     __shared__ int wsum[32];
     const int i = blockIdx.x * 1024 + threadIdx.x;
     int keep = 0, j = 0;
@@ -264,8 +358,10 @@ __host__ __device__ __forceinline__ int wide_chunks(int nnz, int max_chunks)
 }
 __global__ void __launch_bounds__(WT) wide_ax_kernel(const float* __restrict__ X, i64 ldx, i64 n, const int* __restrict__ supp,
                                                      const int* __restrict__ nnz_dev, int max_chunks,
-                                                     const float* __restrict__ x, float* __restrict__ part)
+                                                     const float* __restrict__ x, float* __restrict__ part,
+                                                     const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl && ctl->stop) return;
     __shared__ int sj[WT];
     __shared__ float sv[WT];
     const int nnz = *nnz_dev;                             // exact; the grid was sized from an upper bound
@@ -297,8 +393,10 @@ __global__ void __launch_bounds__(WT) wide_ax_kernel(const float* __restrict__ X
 __global__ void __launch_bounds__(WT) wide_zstep_kernel(const float* __restrict__ part, const int* __restrict__ nnz_dev, int max_chunks, i64 n,
                                                         const float* __restrict__ ydat,
                                                         float frho, float den, float* __restrict__ Ax, float* __restrict__ z,
-                                                        float* __restrict__ y, float* __restrict__ psums)
+                                                        float* __restrict__ y, float* __restrict__ psums,
+                                                        const WideCtl* __restrict__ ctl = nullptr)
 {
+    if (ctl) { if (ctl->stop) return; frho = ctl->frho; den = ctl->den; }
     const int chunks = wide_chunks(*nnz_dev, max_chunks);
     const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
     float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -556,6 +654,11 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     int max_chunks = 64;
     DevBuf<float> part((size_t)max_chunks * (size_t)n);
     int cur_supp = 0, nnz = 0, nnz_bound = 0;
+    // runs of active-set steps are enqueued as batches with device-side loop control (B200ADMM_WIDE_BATCH=0: host-driven)
+    const char* batch_env = getenv("B200ADMM_WIDE_BATCH");
+    const bool batched = !(batch_env && !strcmp(batch_env, "0"));
+    DevBuf<WideCtl> ctl(1);
+    DevBuf<double> trace_dev;
 
     auto compact = [&](const int* src, int len, int* dst) {
         const int nb = (len + 1023) / 1024;
@@ -589,8 +692,61 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
         }
         unsigned iter_counter = 0;                                                // init / init_warm
         const bool tracing = tr.buf && tr.cap > 0 && tr.which == k;
+        if (tracing && batched && !trace_dev.p) trace_dev.alloc((size_t)5 * tr.cap);
         int i;
-        for (i = 0; i < rq.opts.maxit; i++) {
+        for (i = 0; i < rq.opts.maxit; ) {
+            // ---------------- a run of active-set steps as one batch (device-side loop control) ----------------
+            {
+                const bool shortcut = !rq.enet && (double)lambda > (double)lambda0 - 1e-5;
+                auto regular_at = [&](unsigned c) { return is_regular_update(c) && (!rq.enet || lambda < lambda0); };
+                if (batched && !shortcut && nnz > 0 && !regular_at(iter_counter)) {
+                    int cnt = 0;
+                    while (cnt < 64 && i + cnt < rq.opts.maxit && !regular_at(iter_counter + (unsigned)cnt)) cnt++;
+                    WideCtl hc;
+                    memset(&hc, 0, sizeof hc);
+                    hc.rho = rho; hc.sAx2 = sAx2; hc.sz2 = sz2; hc.sy2 = sy2;
+                    CUDA_CHECK(cudaMemcpyAsync(ctl.p, &hc, sizeof hc, cudaMemcpyHostToDevice, s));
+                    WideCtlConst kc;
+                    kc.eps_abs = eps_abs; kc.eps_rel = eps_rel; kc.sqrt_n = std::sqrt((double)n); kc.sqrt_p = std::sqrt((double)p);
+                    kc.lambda = (double)lambda; kc.gamma = gamma; kc.sqrt_sprad = sqrt_sprad; kc.alpha_f = alpha_f;
+                    kc.enet = rq.enet ? 1 : 0; kc.i_start = i; kc.n = (long long)n;
+                    wide_ctl_init_kernel<<<1, 32, 0, s>>>(ctl.p, kc, nnz_dev.p); KERNEL_CHECK();
+                    WideProx q;
+                    q.enet = rq.enet ? 1 : 0; q.pen_d = 0; q.pen_f = 0; q.thresh = 0; q.denom = 1;     // (parameters come from the control block)
+                    const int ablocks = std::min((nnz + 7) / 8, sm_count() * 8);
+                    const int nb = (nnz + 1023) / 1024;
+                    const int chunks_bound = wide_chunks(nnz, max_chunks);
+                    int cs = cur_supp;
+                    for (int b = 0; b < cnt; b++) {
+                        wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, 0.f, gamma, 1, n, tmp.p, ctl.p); KERNEL_CHECK();
+                        wide_active_kernel<<<ablocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cs].p, nnz, x.p, q, ctl.p); KERNEL_CHECK();
+                        compact_count_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, ctl.p); KERNEL_CHECK();
+                        compact_scan_kernel<<<1, 1024, 0, s>>>(counts.p, nb, nnz_dev.p, ctl.p); KERNEL_CHECK();
+                        compact_scatter_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, supp[cs ^ 1].p, ctl.p); KERNEL_CHECK();
+                        cs ^= 1;
+                        wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks_bound), WT, 0, s>>>(X, ldx, n, supp[cs].p, nnz_dev.p, max_chunks, x.p, part.p, ctl.p);
+                        KERNEL_CHECK();
+                        wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, 0.f, 0.f, Ax.p, z.p, y.p, psums.p, ctl.p); KERNEL_CHECK();
+                        wide_control_kernel<<<1, 192, 0, s>>>(ctl.p, kc, psums.p, zblocks, nnz_dev.p, tracing ? trace_dev.p : nullptr, tracing ? tr.cap : 0);
+                        KERNEL_CHECK();
+                    }
+                    CUDA_CHECK(cudaMemcpyAsync(&hc, ctl.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+                    CUDA_CHECK(cudaStreamSynchronize(s));
+                    const int done = hc.iters;
+                    if (tracing && done > 0 && i < tr.cap) {
+                        const int rows = std::min(done, tr.cap - i);
+                        CUDA_CHECK(cudaMemcpy(tr.buf + 5 * (size_t)i, trace_dev.p + 5 * (size_t)i, sizeof(double) * 5 * rows, cudaMemcpyDeviceToHost));
+                        if (tr.nrows) *tr.nrows = i + rows;
+                    }
+                    rho = hc.rho; sAx2 = hc.sAx2; sz2 = hc.sz2; sy2 = hc.sy2; nnz = hc.nnz; nnz_bound = nnz;
+                    cur_supp ^= (done & 1);
+                    iter_counter += (unsigned)done;
+                    work_bytes += hc.work_bytes; work_active += done;
+                    if (hc.stop) { i += done - 1; break; }               // converged at iteration index i + done - 1
+                    i += done;
+                    continue;
+                }
+            }
             const double eps_primal = std::max((double)std::sqrt((float)sAx2), (double)std::sqrt((float)sz2)) * eps_rel + std::sqrt((double)n) * eps_abs;
             const double eps_dual = (double)(sqrt_sprad * std::sqrt((float)sy2)) * eps_rel + std::sqrt((double)p) * eps_abs;
             const float frho = (float)rho;
@@ -683,6 +839,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             }
             if (resid_primal < eps_primal && resid_dual < eps_dual) break;
             if (i > 3) balance_rho(rho, resid_primal, eps_primal, resid_dual, eps_dual);
+            i++;
         }
         out->niter[k] = i + 1;
         out->lambda[k] = lam[k];

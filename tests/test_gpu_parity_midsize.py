@@ -230,6 +230,34 @@ def test_wide_screened_regular_steps_are_bit_identical(A, monkeypatch, n, p, mod
     assert int(out["1"][1].max()) > 16                     # several regular steps (iterations 0, 3, 15, ...) per lambda
 
 
+@pytest.mark.parametrize("n,p,model,alpha,maxit", [(2000, 20000, "lasso", 1.0, 10000), (301, 6000, "lasso", 1.0, 10000),
+                                                  (640, 9000, "enet", 0.4, 10000), (500, 3000, "lasso", 1.0, 37)])
+def test_wide_batched_active_set_steps_are_bit_identical(A, monkeypatch, n, p, model, alpha, maxit):
+    """Runs of active-set steps are enqueued as batches whose stopping rule, rho balancing and prox parameters are
+    evaluated on the device (admm_wide.cu: wide_control_kernel): coefficients, iteration counts (incl. a path that runs out
+    of iterations: maxit = 37 -> 38), the final rho and the whole trace must equal the host-driven loop
+    (B200ADMM_WIDE_BATCH=0) bit for bit."""
+    from admm_b200 import _capi as K
+    rng = np.random.default_rng(n + p + maxit)
+    x = np.asfortranarray(rng.normal(0.2, 2.0, size=(n, p)).astype(np.float32))
+    b = np.zeros(p)
+    b[rng.choice(p, 15, replace=False)] = rng.uniform(0.5, 1.5, size=15)
+    y = (1.0 + x @ b + rng.normal(size=n)).astype(np.float32)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200ADMM_WIDE_BATCH", mode)
+        with K.trace(which=6, cap=2000) as tr:
+            m = A.admm_lasso(x, y).penalty(nlambda=10) if model == "lasso" else A.admm_enet(x, y).penalty(nlambda=10, alpha=alpha)
+            f = m.opts(maxit=maxit).fit()
+        out[mode] = (dense(f.beta), f.niter.copy(), tr.rows.copy(), f.info["rho"])
+    assert np.array_equal(out["1"][1], out["0"][1]), (out["1"][1], out["0"][1])
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert out["1"][2].shape == out["0"][2].shape and np.array_equal(out["1"][2], out["0"][2])
+    assert out["1"][3] == out["0"][3]
+    if maxit == 37:
+        assert (out["1"][1] == 38).any()
+
+
 def test_lad_n20000_p300(A, O):
     rng = np.random.default_rng(8)
     n, p = 20_000, 300

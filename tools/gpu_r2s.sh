@@ -3,12 +3,12 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-( timeout 900 python -m pytest tests/test_gpu_models.py tests/test_gpu_parity_midsize.py tests/test_gpu_kernels.py -m gpu -q -k "wide or gemm_f64" ) > $O/r2s_pytest.log 2>&1
+( timeout 900 python -m pytest tests/test_gpu_models.py tests/test_gpu_parity_midsize.py tests/test_gpu_kernels.py -m gpu -q -k "wide or gemm_f64 or readme" ) > $O/r2s_pytest.log 2>&1
 echo "pytest rc=$?" >> $O/r2s_pytest.log
 tail -n 3 $O/r2s_pytest.log
 timeout 600 python bench.py --config wide --no-cpu > $O/r2s_config_wide.json 2> $O/r2s_config_wide.err
 echo "wide rc=$?"
-B200ADMM_WIDE_SCREEN=0 timeout 600 python bench.py --config wide --no-cpu --no-e2e > $O/r2s_config_wide_unscreened.json 2> $O/r2s_config_wide_unscreened.err
+B200ADMM_WIDE_BATCH=0 timeout 600 python bench.py --config wide --no-cpu --no-e2e > $O/r2s_config_wide_unscreened.json 2> $O/r2s_config_wide_unscreened.err
 python - <<'P'
 import json
 for f in ("r2s_config_wide", "r2s_config_wide_unscreened"):
