@@ -247,8 +247,10 @@ __global__ void wide_ctl_init_kernel(WideCtl* c, WideCtlConst k, const int* __re
     }
 }
 // end of an iteration: sums -> tolerances, residuals, stopping rule, rho balancing, next parameters, trace row
-__global__ void wide_control_kernel(WideCtl* c, WideCtlConst k, const float* __restrict__ psums, int nblocks, const int* __restrict__ nnz_dev,
-                                    double* __restrict__ trace, int trace_cap)
+__global__ void __launch_bounds__(1024) wide_control_kernel(WideCtl* c, WideCtlConst k, const float* __restrict__ psums, int nblocks,
+                                                            const int* __restrict__ nnz_dev, double* __restrict__ trace, int trace_cap,
+                                                            const float* __restrict__ Ax, const float* __restrict__ z, const float* __restrict__ y,
+                                                            float* __restrict__ tmp)
 {
     __shared__ double h[5];
     if (c->stop) return;
@@ -260,7 +262,7 @@ __global__ void wide_control_kernel(WideCtl* c, WideCtlConst k, const float* __r
         if (lane == 0) h[q] = s;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x == 0) {
     const int i = k.i_start + c->iters;
     const double eps_primal = fmax((double)sqrtf((float)c->sAx2), (double)sqrtf((float)c->sz2)) * k.eps_rel + k.sqrt_n * k.eps_abs;
     const double eps_dual = (double)(k.sqrt_sprad * sqrtf((float)c->sy2)) * k.eps_rel + k.sqrt_p * k.eps_abs;
@@ -277,16 +279,59 @@ __global__ void wide_control_kernel(WideCtl* c, WideCtlConst k, const float* __r
         row[0] = eps_primal; row[1] = resid_primal; row[2] = eps_dual; row[3] = resid_dual; row[4] = rho;
     }
     c->iters += 1;
-    if (resid_primal < eps_primal && resid_dual < eps_dual) { c->stop = 1; return; }
-    if (i > 3) {
-        double r = rho;                                                       // balance_rho
-        if (resid_primal / eps_primal > 10 * resid_dual / eps_dual) r *= 2;
-        else if (resid_dual / eps_dual > 10 * resid_primal / eps_primal) r /= 2;
-        if (resid_primal < eps_primal) r /= 1.2;
-        if (resid_dual < eps_dual) r *= 1.2;
-        c->rho = r;
+    if (resid_primal < eps_primal && resid_dual < eps_dual) c->stop = 1;
+    else {
+        if (i > 3) {
+            double r = rho;                                                   // balance_rho
+            if (resid_primal / eps_primal > 10 * resid_dual / eps_dual) r *= 2;
+            else if (resid_dual / eps_dual > 10 * resid_primal / eps_primal) r /= 2;
+            if (resid_primal < eps_primal) r /= 1.2;
+            if (resid_dual < eps_dual) r *= 1.2;
+            c->rho = r;
+        }
+        wide_derive_params(c, k);
     }
-    wide_derive_params(c, k);
+    }
+    __syncthreads();
+    // tmp of the NEXT active-set step with the new rho (what wide_tmp_kernel computes: one launch less per iteration)
+    if (c->stop || tmp == nullptr) return;
+    const float frho = c->frho;
+    for (long long i = threadIdx.x; i < k.n; i += blockDim.x) tmp[i] = ((Ax[i] + z[i]) + y[i] / frho) / k.gamma;
+}
+
+// single-CTA stable compaction for short candidate lists (<= a few thousand entries: the active-set steps): the three
+// launches of the general scheme cost more in launch latency than in work
+__global__ void __launch_bounds__(1024) compact_small_kernel(const int* __restrict__ src, const float* __restrict__ x, int len,
+                                                             int* __restrict__ out, int* __restrict__ total, const WideCtl* __restrict__ ctl)
+{
+    if (ctl) { if (ctl->stop) return; len = ctl->nnz; }
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < len; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        int keep = 0, j = 0;
+        if (i < len) { j = src[i]; keep = x[j] != 0.f; }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(ballot);
+        __syncthreads();
+        int chunk_total = 0;
+        if (warp == 0) {
+            int v = wsum[lane];
+            const int mine = v;
+            for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += t; }
+            wsum[lane] = v - mine;                                   // exclusive warp offsets
+            chunk_total = __shfl_sync(0xffffffffu, v, 31);
+        }
+        __syncthreads();
+        if (keep) out[base + wsum[warp] + __popc(ballot & ((1u << lane) - 1u))] = j;
+        __syncthreads();
+        if (threadIdx.x == 0) base += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = base;
 }
 
 // ---- stable compaction of "x[j] != 0" into a sorted index list ---------------------------------
@@ -717,17 +762,23 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                     const int nb = (nnz + 1023) / 1024;
                     const int chunks_bound = wide_chunks(nnz, max_chunks);
                     int cs = cur_supp;
+                    // five launches per iteration: x-update, compaction, Ax partials, z-step, control (+ the next tmp)
+                    wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, 0.f, gamma, 1, n, tmp.p, ctl.p); KERNEL_CHECK();
                     for (int b = 0; b < cnt; b++) {
-                        wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, 0.f, gamma, 1, n, tmp.p, ctl.p); KERNEL_CHECK();
                         wide_active_kernel<<<ablocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cs].p, nnz, x.p, q, ctl.p); KERNEL_CHECK();
-                        compact_count_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, ctl.p); KERNEL_CHECK();
-                        compact_scan_kernel<<<1, 1024, 0, s>>>(counts.p, nb, nnz_dev.p, ctl.p); KERNEL_CHECK();
-                        compact_scatter_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, supp[cs ^ 1].p, ctl.p); KERNEL_CHECK();
+                        if (nnz <= 8192) {
+                            compact_small_kernel<<<1, 1024, 0, s>>>(supp[cs].p, x.p, nnz, supp[cs ^ 1].p, nnz_dev.p, ctl.p); KERNEL_CHECK();
+                        } else {
+                            compact_count_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, ctl.p); KERNEL_CHECK();
+                            compact_scan_kernel<<<1, 1024, 0, s>>>(counts.p, nb, nnz_dev.p, ctl.p); KERNEL_CHECK();
+                            compact_scatter_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, supp[cs ^ 1].p, ctl.p); KERNEL_CHECK();
+                        }
                         cs ^= 1;
                         wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks_bound), WT, 0, s>>>(X, ldx, n, supp[cs].p, nnz_dev.p, max_chunks, x.p, part.p, ctl.p);
                         KERNEL_CHECK();
                         wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, 0.f, 0.f, Ax.p, z.p, y.p, psums.p, ctl.p); KERNEL_CHECK();
-                        wide_control_kernel<<<1, 192, 0, s>>>(ctl.p, kc, psums.p, zblocks, nnz_dev.p, tracing ? trace_dev.p : nullptr, tracing ? tr.cap : 0);
+                        wide_control_kernel<<<1, 1024, 0, s>>>(ctl.p, kc, psums.p, zblocks, nnz_dev.p, tracing ? trace_dev.p : nullptr, tracing ? tr.cap : 0,
+                                                               Ax.p, z.p, y.p, b + 1 < cnt ? tmp.p : nullptr);
                         KERNEL_CHECK();
                     }
                     CUDA_CHECK(cudaMemcpyAsync(&hc, ctl.p, sizeof hc, cudaMemcpyDeviceToHost, s));
