@@ -223,6 +223,77 @@ __global__ void __launch_bounds__(WT) wide_prox_list_kernel(const float* __restr
     x[j] = prox_regular(v, q);
 }
 
+// ---- fused active-set step: x-update and the new A x from ONE read of the support columns ------------------
+// wide_active_kernel + wide_ax_kernel read every support column twice (dot product with tmp, then the row-parallel sum
+// A x), both as gathers at about half the HBM rate.  Here a CTA owns a contiguous range of the support list; its 512
+// threads hold a column in registers (thread t: rows 4 (t + 512 v) .. + 3), reduce the dot product across the CTA,
+// apply the prox and add x_j times the SAME registers to the CTA's partial A x; the next column is loaded while the
+// reduction of the current one runs.  part[b][0 .. n) = partial of logical CTA b; wide_zstep_kernel adds the
+// min(SMs, nnz) partials in CTA order.  The partition depends on the support size only (not on the launch bound), so
+// batched and host-driven runs stay bit-identical.
+constexpr int FT = 512;
+__host__ __device__ __forceinline__ int wide_fused_ctas(int nnz, int sms) { return nnz < sms ? nnz : sms; }
+template <int NV>
+__global__ void __launch_bounds__(FT, 1) wide_active_ax_kernel(const float* __restrict__ X, i64 ldx, i64 n, const float* __restrict__ tmp,
+                                                               const int* __restrict__ supp, int nnz, int sms, float* __restrict__ x, WideProx q,
+                                                               float* __restrict__ part, const WideCtl* __restrict__ ctl)
+{
+    __shared__ float scratch[33];
+    if (ctl) {
+        if (ctl->stop) return;
+        nnz = ctl->nnz; q.pen_f = ctl->pen_f; q.thresh = ctl->thresh; q.denom = ctl->denom;
+    }
+    const int G = wide_fused_ctas(nnz, sms);
+    if ((int)blockIdx.x >= G) return;
+    const int per = (nnz + G - 1) / G;
+    const int k0 = blockIdx.x * per, k1 = min(nnz, k0 + per);
+    const int n4 = (int)(n / 4);                              // (n % 4 == 0: checked by the caller)
+    const int tid = threadIdx.x;
+    float4 t[NV], acc[NV], c[NV], cn[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const int idx = tid + v * FT;
+        t[v] = idx < n4 ? __ldg(reinterpret_cast<const float4*>(tmp) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    auto load_col = [&](int k, float4 (&dst)[NV]) {
+        const float4* col = reinterpret_cast<const float4*>(X + (i64)supp[k] * ldx);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const int idx = tid + v * FT;
+            dst[v] = idx < n4 ? ld_stream_f4(col + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (k0 < k1) load_col(k0, c);
+    for (int k = k0; k < k1; k++) {
+        if (k + 1 < k1) load_col(k + 1, cn);
+        float d = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            d = fmaf(c[v].x, t[v].x, d); d = fmaf(c[v].y, t[v].y, d); d = fmaf(c[v].z, t[v].z, d); d = fmaf(c[v].w, t[v].w, d);
+        }
+        d = block_sum(d, scratch);
+        const int j = supp[k];
+        const float xn = prox_active(x[j] - d, q);
+        __syncthreads();                                      // everybody has read x[j]
+        if (tid == 0) x[j] = xn;
+        if (xn != 0.f) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                acc[v].x += c[v].x * xn; acc[v].y += c[v].y * xn; acc[v].z += c[v].z * xn; acc[v].w += c[v].w * xn;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) c[v] = cn[v];
+    }
+    float4* dst = reinterpret_cast<float4*>(part + (size_t)blockIdx.x * (size_t)n);
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const int idx = tid + v * FT;
+        if (idx < n4) dst[idx] = acc[v];
+    }
+}
+
 // ---- device-side loop control for runs of active-set steps ---------------------------------------------------
 // Between two regular steps (iteration counters 4^k - 1) every iteration is an active-set step whose launch shapes are
 // bounded by the support size at the start of the run (the support only shrinks).  Such a run is enqueued as ONE batch
@@ -439,10 +510,11 @@ __global__ void __launch_bounds__(WT) wide_zstep_kernel(const float* __restrict_
                                                         const float* __restrict__ ydat,
                                                         float frho, float den, float* __restrict__ Ax, float* __restrict__ z,
                                                         float* __restrict__ y, float* __restrict__ psums,
-                                                        const WideCtl* __restrict__ ctl = nullptr)
+                                                        const WideCtl* __restrict__ ctl = nullptr, int fused_nnz = -1, int sms = 0)
 {
-    if (ctl) { if (ctl->stop) return; frho = ctl->frho; den = ctl->den; }
-    const int chunks = wide_chunks(*nnz_dev, max_chunks);
+    if (ctl) { if (ctl->stop) return; frho = ctl->frho; den = ctl->den; if (fused_nnz >= 0) fused_nnz = ctl->nnz; }
+    // after a fused active-set step the partials are those of its logical CTAs (support size BEFORE the step)
+    const int chunks = fused_nnz >= 0 ? wide_fused_ctas(fused_nnz, sms) : wide_chunks(*nnz_dev, max_chunks);
     const i64 i = (i64)blockIdx.x * WT + threadIdx.x;
     float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (i < n) {
@@ -697,7 +769,18 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
     DevBuf<float> psums((size_t)zblocks * 5);
     DevBuf<double> sums6(6);
     int max_chunks = 64;
-    DevBuf<float> part((size_t)max_chunks * (size_t)n);
+    const int sms_n = sm_count();
+    DevBuf<float> part((size_t)std::max(max_chunks, sms_n) * (size_t)n);
+    // fused active-set step (x-update + A x from one read of the support columns): columns of up to 12288 floats, 16-byte aligned
+    const char* fuse_env = getenv("B200ADMM_WIDE_FUSE");
+    const bool fused_ok = !(fuse_env && !strcmp(fuse_env, "0")) && n % 4 == 0 && n <= 4 * FT * 6 && (((uintptr_t)X) & 15) == 0;
+    auto launch_fused = [&](int grid, const int* supp_p, int nnz_arg, const WideProx& qq, const WideCtl* cp) {
+        const int nv = (int)((n / 4 + FT - 1) / FT);
+        if (nv <= 2) wide_active_ax_kernel<2><<<grid, FT, 0, s>>>(X, ldx, n, tmp.p, supp_p, nnz_arg, sms_n, x.p, qq, part.p, cp);
+        else if (nv <= 4) wide_active_ax_kernel<4><<<grid, FT, 0, s>>>(X, ldx, n, tmp.p, supp_p, nnz_arg, sms_n, x.p, qq, part.p, cp);
+        else wide_active_ax_kernel<6><<<grid, FT, 0, s>>>(X, ldx, n, tmp.p, supp_p, nnz_arg, sms_n, x.p, qq, part.p, cp);
+        KERNEL_CHECK();
+    };
     int cur_supp = 0, nnz = 0, nnz_bound = 0;
     // runs of active-set steps are enqueued as batches with device-side loop control (B200ADMM_WIDE_BATCH=0: host-driven)
     const char* batch_env = getenv("B200ADMM_WIDE_BATCH");
@@ -765,7 +848,8 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                     // five launches per iteration: x-update, compaction, Ax partials, z-step, control (+ the next tmp)
                     wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, 0.f, gamma, 1, n, tmp.p, ctl.p); KERNEL_CHECK();
                     for (int b = 0; b < cnt; b++) {
-                        wide_active_kernel<<<ablocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cs].p, nnz, x.p, q, ctl.p); KERNEL_CHECK();
+                        if (fused_ok) launch_fused(std::min(sms_n, nnz), supp[cs].p, nnz, q, ctl.p);
+                        else { wide_active_kernel<<<ablocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cs].p, nnz, x.p, q, ctl.p); KERNEL_CHECK(); }
                         if (nnz <= 8192) {
                             compact_small_kernel<<<1, 1024, 0, s>>>(supp[cs].p, x.p, nnz, supp[cs ^ 1].p, nnz_dev.p, ctl.p); KERNEL_CHECK();
                         } else {
@@ -774,9 +858,14 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                             compact_scatter_kernel<<<nb, 1024, 0, s>>>(supp[cs].p, x.p, nnz, counts.p, supp[cs ^ 1].p, ctl.p); KERNEL_CHECK();
                         }
                         cs ^= 1;
-                        wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks_bound), WT, 0, s>>>(X, ldx, n, supp[cs].p, nnz_dev.p, max_chunks, x.p, part.p, ctl.p);
-                        KERNEL_CHECK();
-                        wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, 0.f, 0.f, Ax.p, z.p, y.p, psums.p, ctl.p); KERNEL_CHECK();
+                        if (fused_ok) {
+                            wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, 0.f, 0.f, Ax.p, z.p, y.p, psums.p, ctl.p, 0, sms_n);
+                            KERNEL_CHECK();
+                        } else {
+                            wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks_bound), WT, 0, s>>>(X, ldx, n, supp[cs].p, nnz_dev.p, max_chunks, x.p, part.p, ctl.p);
+                            KERNEL_CHECK();
+                            wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, 0.f, 0.f, Ax.p, z.p, y.p, psums.p, ctl.p); KERNEL_CHECK();
+                        }
                         wide_control_kernel<<<1, 1024, 0, s>>>(ctl.p, kc, psums.p, zblocks, nnz_dev.p, tracing ? trace_dev.p : nullptr, tracing ? tr.cap : 0,
                                                                Ax.p, z.p, y.p, b + 1 < cnt ? tmp.p : nullptr);
                         KERNEL_CHECK();
@@ -803,6 +892,7 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             const float frho = (float)rho;
             const int nnz_before = nnz;
             int step_kind = 0;                                             // 0: x = 0 shortcut, 1: regular, 2: active set
+            bool fused_step = false;                                       // this iteration's A x partials come from the fused active-set kernel
             // ---------------- x step ----------------
             if (!rq.enet && (double)lambda > (double)lambda0 - 1e-5) {
                 if (nnz > 0) { x.zero(s); nnz = 0; CUDA_CHECK(cudaMemsetAsync(nnz_dev.p, 0, sizeof(int), s)); }
@@ -851,8 +941,11 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
                     q.denom = (float)(1.0 + (double)q.pen_f * (1.0 - (double)alpha_f));
                     if (nnz > 0) {
                         wide_tmp_kernel<<<zblocks, WT, 0, s>>>(Ax.p, z.p, y.p, frho, gamma, 1, n, tmp.p); KERNEL_CHECK();
-                        const int blocks = std::min((nnz + 7) / 8, sm_count() * 8);
-                        wide_active_kernel<<<blocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cur_supp].p, nnz, x.p, q); KERNEL_CHECK();
+                        if (fused_ok) { launch_fused(std::min(sms_n, nnz), supp[cur_supp].p, nnz, q, nullptr); fused_step = true; }
+                        else {
+                            const int blocks = std::min((nnz + 7) / 8, sm_count() * 8);
+                            wide_active_kernel<<<blocks, WT, 0, s>>>(X, ldx, n, tmp.p, supp[cur_supp].p, nnz, x.p, q); KERNEL_CHECK();
+                        }
                         compact(supp[cur_supp].p, nnz, supp[cur_supp ^ 1].p);
                         cur_supp ^= 1;
                     }
@@ -865,11 +958,17 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
             }
             // ---------------- z step, residual, dual update ----------------
             const int chunks_bound = wide_chunks(nnz_bound, max_chunks);
+            if (fused_step) {
+                // (the partial A x of the fused step's logical CTAs are already in `part`)
+                wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, frho, (float)(-1 - rho), Ax.p, z.p, y.p, psums.p, nullptr, nnz_before, sms_n);
+                KERNEL_CHECK();
+            } else {
             if (chunks_bound > 0) {
                 wide_ax_kernel<<<dim3((unsigned)zblocks, (unsigned)chunks_bound), WT, 0, s>>>(X, ldx, n, supp[cur_supp].p, nnz_dev.p, max_chunks, x.p, part.p);
                 KERNEL_CHECK();
             }
             wide_zstep_kernel<<<zblocks, WT, 0, s>>>(part.p, nnz_dev.p, max_chunks, n, ydat.p, frho, (float)(-1 - rho), Ax.p, z.p, y.p, psums.p); KERNEL_CHECK();
+            }
             wide_finish_sums_kernel<<<1, 192, 0, s>>>(psums.p, zblocks, nnz_dev.p, sums6.p); KERNEL_CHECK();
             double h[6];
             CUDA_CHECK(cudaMemcpyAsync(h, sums6.p, sizeof h, cudaMemcpyDeviceToHost, s));
