@@ -11,6 +11,7 @@
 // bypass L1; the vector operand stays in L1/L2.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -148,8 +149,10 @@ void gemv_t(cudaStream_t s, const T* A, i64 m, i64 ncol, i64 lda, const T* v, T*
         // 4.2 waves cost 5; LAD's X'v ran at 67 % of the HBM rate).  Columns are therefore cut into row segments
         // until there are ~16 waves of CTAs; the segment sums are added in segment order (deterministic).
         const i64 slots = (i64)sms * 8;
-        const int nseg = (int)std::max<i64>(1, std::min<i64>(8, (16 * slots + ncol - 1) / ncol));
-        if (nseg > 1 && ncol * nseg < ((i64)1 << 30)) {
+        // (at least two segments: with one CTA per whole column the 8e4 x 8e4 product of the consensus solver ran at 5.39 TB/s,
+        // cut in two at 6.77 TB/s -- profiles/r2x_gemv_nseg.log)
+        const int nseg = (int)std::max<i64>(2, std::min<i64>(8, (16 * slots + ncol - 1) / ncol));
+        if (ncol * nseg < ((i64)1 << 30)) {
             const i64 seg_len = (((m + nseg - 1) / nseg) + 3) & ~(i64)3;
             DevBuf<T> partial((size_t)ncol * nseg);
             gemv_t_seg_kernel<T><<<(unsigned)(ncol * nseg), 256, 0, s>>>(A, m, lda, v, nseg, seg_len, partial.p);
