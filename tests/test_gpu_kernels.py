@@ -77,7 +77,9 @@ def test_gram_cuda_cores(K, torch, n, p):
 
 def test_gemv_t(K, torch):
     rng = np.random.default_rng(4)
-    for m, nc in [(100000, 7), (1000, 1000), (37, 5), (40001, 3)]:
+    # (33001 x 9600: long columns AND more columns than CTA slots -- the shape class of the consensus solver's K_i^-1 product,
+    #  cut into two row segments per column; odd length: scalar tail)
+    for m, nc in [(100000, 7), (1000, 1000), (37, 5), (40001, 3), (33001, 9600)]:
         a = rng.normal(size=(m, nc)).astype(np.float32)
         v = rng.normal(size=m).astype(np.float32)
         ad, vd = colmajor_dev(torch, a), torch.from_numpy(v).cuda()
