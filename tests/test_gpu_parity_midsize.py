@@ -278,7 +278,7 @@ def test_bp_n500_p5000(A, O):
     residual c is the SAME number each time and the restart rule `c < 0.999 * c_old` (src/FADMMBase.h:243) compares
     c with 0.999 * (c / 0.999) -- equal in exact arithmetic, decided by the last bit of |r|^2 in floating point.  Two
     correct implementations that sum the norm in different orders take different restart / rho-balancing branches
-    from there on (measured here: rho 2.4 vs 3.456 at iteration 8, 191 vs 214 iterations; tools/debug_bp_trace.py).
+    from there on (measured here: rho 2.4 vs 3.456 at iteration 8, 191 vs 214 iterations; tests/tools/debug_bp_trace.py).
     What is asserted instead: the rows before the first such decision agree to 1e-9, and both runs end at the same
     basis-pursuit solution within the solver's own stopping tolerance (eps 1e-4 relative): feasible, l1 norm not above
     the planted signal's, coefficients within 2e-2 of each other and of the planted signal."""

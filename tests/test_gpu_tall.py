@@ -7,7 +7,7 @@ Tolerances (stated): float32 path, same (X, y, lambda, rho
     The stopping rule accepts any iterate with |r|_2 < sqrt(p) eps_abs + eps_rel |x|_2 (eps = 1e-5), so two
     runs that stop an iteration apart -- GPU and CPU differ in the summation order of the norms, of the
     K^-1 product and of the Gram matrix -- may differ by that much; measured over six problems
-    (tools/parity_modes.py, p = 200 .. 1024): up to 1.3e-4 with the TF32 Gram split, 2.2e-4 with the
+    (tests/tools/parity_modes.py, p = 200 .. 1024): up to 1.3e-4 with the TF32 Gram split, 2.2e-4 with the
     fp16 split (whose Gram matrix is the closer of the two to float64);
   * support identical except coordinates whose magnitude is below 1e-4 in either solution;
   * per-iteration scalars (eps, residuals) within 1e-3 relative over the first iterations;

@@ -1,4 +1,4 @@
-"""Debug: where do the GPU and oracle BP traces part?  python tools/debug_bp_trace.py"""
+"""Debug: where do the GPU and oracle BP traces part?  python tests/tools/debug_bp_trace.py"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")

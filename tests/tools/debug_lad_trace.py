@@ -1,5 +1,5 @@
 """Debug: where do the GPU and oracle LAD / BP traces part on bench.py's generator?
-python tools/debug_lad_trace.py [lad|bp] n p [maxit]"""
+python tests/tools/debug_lad_trace.py [lad|bp] n p [maxit]"""
 import sys
 import time
 import numpy as np

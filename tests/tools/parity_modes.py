@@ -1,6 +1,6 @@
 """GPU fit vs CPU oracle for the tall test problems under each Gram kernel (run on the GPU box, one
 process per mode because the mode is read from the environment):
-    B200ADMM_GRAM=tf32 python tools/parity_modes.py ; python tools/parity_modes.py"""
+    B200ADMM_GRAM=tf32 python tests/tools/parity_modes.py ; python tests/tools/parity_modes.py"""
 import os
 import sys
 
