@@ -741,14 +741,19 @@ void solve_wide(const LassoRequest& rq, b200admm_path* out)
 
     // ---- fp16 copy + column norms for the screened regular steps (see wide_screen_kernel) -----------------------
     const char* screen_env = getenv("B200ADMM_WIDE_SCREEN");
-    const bool screen = !(screen_env && !strcmp(screen_env, "0")) && gemv_t_uses_warp_kernel(n) && p >= 4096 && p < 2147483647LL;
+    bool screen = !(screen_env && !strcmp(screen_env, "0")) && gemv_t_uses_warp_kernel(n) && p >= 4096 && p < 2147483647LL;
     const i64 ldh = (n + 7) & ~(i64)7;
     DevBuf<__half> Xh;
     DevBuf<float> colnorm, tmpnorm;
     DevBuf<int> cand;
     if (screen) {
+        // (the half-precision copy is an optimisation: a design that leaves no room for it runs unscreened)
+        try { Xh.alloc((size_t)ldh * (size_t)p); }
+        catch (const CodeError&) { screen = false; }
+    }
+    if (screen) {
         tm.start();
-        Xh.alloc((size_t)ldh * (size_t)p); colnorm.alloc(p); tmpnorm.alloc(1); cand.alloc(p);
+        colnorm.alloc(p); tmpnorm.alloc(1); cand.alloc(p);
         wide_half_copy_kernel<<<(unsigned)std::min<i64>((p + 7) / 8, (i64)sm_count() * 16), WT, 0, s>>>(X, ldx, n, p, ldh, Xh.p, colnorm.p);
         KERNEL_CHECK();
         T.factor = tm.stop();                                   // (reported under `factor`: the wide path has no factorisation)
