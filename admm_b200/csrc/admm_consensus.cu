@@ -82,10 +82,50 @@ __global__ void __launch_bounds__(CT) cons_gather_kernel(const float* __restrict
     s = block_sum(s, scratch);
     if (threadIdx.x == 0) *slot_x2 = first ? s : *slot_x2 + s;
 }
+// Device-side loop control (batched passes): the master's bookkeeping of PADMMBase_Master::solve (src/PADMMBase.h:174-237)
+// -- closing the books on iteration t - 1 with the primal residual that arrived with this exchange, the stopping rule,
+// the tolerances of iteration t, the dual residual after the z-update -- in the host loop's own double expressions.
+struct ConsCtl {
+    double sx2, sz2, eps_p, eps_d, rd;     // norms of the current iterate, tolerances / dual residual of the open iteration
+    int have_prev, stop, niter, t, trace_rows;
+};
+struct ConsConst {
+    double eps_abs, eps_rel, sqrt_pN, sqrtN, rho, dN;
+    int maxit;
+};
+
 // z_new = soft(acc / N, pen); out[0] = sum (z_new - z)^2, out[1] = |z_new|^2 ; z <- z_new
-__global__ void __launch_bounds__(CT) cons_z_kernel(const float* __restrict__ acc, float fN, double pen, int p, float* __restrict__ z, float* __restrict__ out2)
+// acc = the exchanged payload (p sums + 3 tail scalars).  With a control block the kernel first closes iteration t - 1.
+__global__ void __launch_bounds__(CT) cons_z_kernel(const float* __restrict__ acc, float fN, double pen, int p, float* __restrict__ z, float* __restrict__ out2,
+                                                    ConsCtl* __restrict__ c = nullptr, ConsConst k = ConsConst(), double* __restrict__ trace = nullptr,
+                                                    int trace_cap = 0)
 {
     __shared__ float scratch[33];
+    __shared__ int s_stop;
+    if (c) {
+        if (threadIdx.x == 0) {
+            if (!c->stop) {
+                const int t = c->t;
+                if (c->have_prev) {
+                    const double rp_prev = sqrt((double)acc[p + 1]);
+                    if (trace && t - 1 < trace_cap) {
+                        double* row = trace + 5 * (size_t)(t - 1);
+                        row[0] = c->eps_p; row[1] = rp_prev; row[2] = c->eps_d; row[3] = c->rd; row[4] = k.rho;
+                        c->trace_rows = t;
+                    }
+                    if (rp_prev < c->eps_p && c->rd < c->eps_d) { c->niter = t; c->stop = 1; }
+                }
+                if (!c->stop && t == k.maxit) c->stop = 1;                 // only closing the books: niter stays maxit + 1
+                if (!c->stop) {
+                    c->eps_p = fmax(sqrt(c->sx2), sqrt(c->sz2) * k.sqrtN) * k.eps_rel + k.sqrt_pN * k.eps_abs;
+                    c->eps_d = sqrt((double)acc[p + 2]) * k.eps_rel + k.sqrt_pN * k.eps_abs;
+                }
+            }
+            s_stop = c->stop;
+        }
+        __syncthreads();
+        if (s_stop) return;
+    }
     float d2 = 0.f, z2 = 0.f;
     for (int j = threadIdx.x; j < p; j += CT) {
         const float v = acc[j] / fN;
@@ -99,13 +139,24 @@ __global__ void __launch_bounds__(CT) cons_z_kernel(const float* __restrict__ ac
     }
     d2 = block_sum(d2, scratch);
     z2 = block_sum(z2, scratch);
-    if (threadIdx.x == 0) { out2[0] = d2; out2[1] = z2; }
+    if (threadIdx.x == 0) {
+        out2[0] = d2; out2[1] = z2;
+        if (c) {
+            c->rd = k.rho * sqrt(k.dN * (double)d2);                       // PADMMLasso.h:151-154
+            c->sz2 = (double)z2;
+            c->sx2 = (double)acc[p];
+            c->have_prev = 1;
+            c->t += 1;
+        }
+    }
 }
 // r = x - z ; y += frho r ; slots: |r|^2, |y|^2
 __global__ void __launch_bounds__(CT) cons_dual_kernel(const float* __restrict__ x, const float* __restrict__ z, float frho, int p, int first,
-                                                       float* __restrict__ y, float* __restrict__ slot_r2, float* __restrict__ slot_y2)
+                                                       float* __restrict__ y, float* __restrict__ slot_r2, float* __restrict__ slot_y2,
+                                                       const ConsCtl* __restrict__ c = nullptr)
 {
     __shared__ float scratch[33];
+    if (c && c->stop) return;
     float r2 = 0.f, y2 = 0.f;
     for (int j = threadIdx.x; j < p; j += CT) {
         const float r = x[j] - z[j];
@@ -311,6 +362,11 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
     const int pi = (int)p;
     // norms of the current iterate: global sum_i |x_i|^2, |z|^2 (sum_i |y_i|^2 arrives with each exchange)
     double sx2 = 0, sz2 = 0;
+    // B200ADMM_CONS_BATCH=0: host-driven loop (two device->host reads per iteration) instead of device-controlled batches
+    const char* cbatch_env = getenv("B200ADMM_CONS_BATCH");
+    const bool batched = !(cbatch_env && !strcmp(cbatch_env, "0"));
+    DevBuf<ConsCtl> ctl(1);
+    DevBuf<double> trace_dev;
 
     tm.start();
     for (int k = 0; k < nl; k++) {
@@ -322,6 +378,54 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
         double eps_p_cur = 0, eps_d_cur = 0, rd_cur = 0;
         bool have_prev = false;
         int niter = rq.opts.maxit + 1;
+        if (batched) {
+            // passes enqueued in batches without host round trips; the stopping rule runs in cons_z_kernel
+            ConsCtl hc;
+            memset(&hc, 0, sizeof hc);
+            hc.sx2 = sx2; hc.sz2 = sz2; hc.niter = rq.opts.maxit + 1;
+            CUDA_CHECK(cudaMemcpyAsync(ctl.p, &hc, sizeof hc, cudaMemcpyHostToDevice, s));
+            ConsConst kc;
+            kc.eps_abs = eps_abs; kc.eps_rel = eps_rel; kc.sqrt_pN = sqrt_pN; kc.sqrtN = std::sqrt((double)N); kc.rho = rho; kc.dN = (double)N;
+            kc.maxit = rq.opts.maxit;
+            if (tracing && !trace_dev.p) trace_dev.alloc((size_t)5 * tr.cap);
+            for (int t0 = 0; t0 <= rq.opts.maxit && !hc.stop; ) {
+                const int cnt = std::min(32, rq.opts.maxit + 1 - t0);
+                for (int b2 = 0; b2 < cnt; b2++) {
+                    for (size_t i = 0; i < blocks.size(); i++) {
+                        Block& b = *blocks[i];
+                        cons_rhs_kernel<<<vg, CT, 0, s>>>(b.Ab.p, b.y.p, z.p, rho, pi, rhs.p); KERNEL_CHECK();
+                        if (b.tall) {
+                            gemv_t<float>(s, b.Kinv.p, p, p, ld, rhs.p, b.x.p);
+                        } else {
+                            const float* A = Xs.p + b.row0;
+                            gemv_n<float>(s, A, b.rows, p, ldx, rhs.p, b.t1.p, b.work.p);
+                            gemv_t<float>(s, b.Kinv.p, b.rows, b.rows, b.rows, b.t1.p, b.t2.p);
+                            gemv_t<float>(s, A, b.rows, p, ldx, b.t2.p, b.x.p);
+                            cons_woodbury_kernel<<<vg, CT, 0, s>>>(rhs.p, b.x.p, frho, pi, b.x.p); KERNEL_CHECK();
+                        }
+                        cons_gather_kernel<<<1, CT, 0, s>>>(b.x.p, b.y.p, frho, pi, i == 0 ? 1 : 0, payload.p, payload.p + p); KERNEL_CHECK();
+                    }
+                    CUDA_CHECK(cudaMemcpyAsync(payload.p + p + 1, local_tail.p, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                    allreduce_sum(s, payload.p, (size_t)p + 3);
+                    cons_z_kernel<<<1, CT, 0, s>>>(payload.p, (float)N, pen, pi, z.p, zout2.p, ctl.p, kc, tracing ? trace_dev.p : nullptr, tracing ? tr.cap : 0);
+                    KERNEL_CHECK();
+                    for (size_t i = 0; i < blocks.size(); i++) {
+                        Block& b = *blocks[i];
+                        cons_dual_kernel<<<1, CT, 0, s>>>(b.x.p, z.p, frho, pi, i == 0 ? 1 : 0, b.y.p, local_tail.p, local_tail.p + 1, ctl.p); KERNEL_CHECK();
+                    }
+                }
+                CUDA_CHECK(cudaMemcpyAsync(&hc, ctl.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+                CUDA_CHECK(cudaStreamSynchronize(s));
+                t0 += cnt;
+            }
+            niter = hc.niter;
+            sx2 = hc.sx2; sz2 = hc.sz2;
+            if (tracing && hc.trace_rows > 0) {
+                const int rows = std::min(hc.trace_rows, tr.cap);
+                CUDA_CHECK(cudaMemcpy(tr.buf, trace_dev.p, sizeof(double) * 5 * rows, cudaMemcpyDeviceToHost));
+                if (tr.nrows) *tr.nrows = rows;
+            }
+        } else
         for (int t = 0; t <= rq.opts.maxit; t++) {
             for (size_t i = 0; i < blocks.size(); i++) {
                 Block& b = *blocks[i];

@@ -203,3 +203,24 @@ def test_consensus_trace_and_maxit(A, O):
     assert np.allclose(tr.rows[:m, [0, 1, 2, 4]], o["trace"][:m][:, [0, 1, 2, 4]], rtol=1e-4, atol=1e-7)
     assert np.allclose(tr.rows[:m, 3], o["trace"][:m, 3], rtol=1e-2, atol=1e-6)   # rho*sqrt(N)*|z+ - z|: float differences of nearly equal z
     assert np.abs(dense(f.beta)[:, 0] - o["beta"][:, 0]).max() < 1e-5
+
+
+@pytest.mark.parametrize("n,p,N,maxit", [(1200, 40, 3, 3000), (90, 120, 2, 3000), (999, 64, 4, 45), (2000, 300, 2, 3000)])
+def test_consensus_batched_passes_are_bit_identical(A, monkeypatch, n, p, N, maxit):
+    """The consensus passes are enqueued in batches and the master's bookkeeping (closing iteration t - 1, stopping rule,
+    tolerances, dual residual) runs in cons_z_kernel: coefficients, iteration counts (incl. a run that exhausts maxit) and
+    the trace must equal the host-driven loop (B200ADMM_CONS_BATCH=0) bit for bit."""
+    from admm_b200 import _capi as K
+    x, y, _ = problem(n, p, seed=n + p + N + 1)
+    lam = [0.4, 0.1, 0.05] if n > p else [0.8, 0.4]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200ADMM_CONS_BATCH", mode)
+        with K.trace(which=1, cap=4000) as tr:
+            f = A.admm_lasso(x, y).penalty(lam).parallel(N).opts(maxit=maxit).fit()
+        out[mode] = (dense(f.beta), f.niter.copy(), tr.rows.copy())
+    assert np.array_equal(out["1"][1], out["0"][1]), (out["1"][1], out["0"][1])
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert out["1"][2].shape == out["0"][2].shape and np.array_equal(out["1"][2], out["0"][2])
+    if maxit == 45:
+        assert (out["1"][1] == 46).any()
