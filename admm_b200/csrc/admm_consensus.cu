@@ -389,7 +389,10 @@ void solve_consensus(const LassoRequest& rq, int nthread, b200admm_path* out)
             kc.maxit = rq.opts.maxit;
             if (tracing && !trace_dev.p) trace_dev.alloc((size_t)5 * tr.cap);
             for (int t0 = 0; t0 <= rq.opts.maxit && !hc.stop; ) {
-                const int cnt = std::min(32, rq.opts.maxit + 1 - t0);
+                // batch length: passes after the converged one are wasted work (each reads every K_i^-1 once), so a batch
+                // is worth about 1.5 ms of device time -- 32 passes at p ~ 1e3, one at p = 8e4 (then still one read, not two)
+                const double est_pass = 4.0 * (double)p * (double)p * (double)blocks.size() / 5e12 + 2e-5;
+                const int cnt = std::min(std::max(1, std::min(32, (int)(1.5e-3 / est_pass))), rq.opts.maxit + 1 - t0);
                 for (int b2 = 0; b2 < cnt; b2++) {
                     for (size_t i = 0; i < blocks.size(); i++) {
                         Block& b = *blocks[i];
