@@ -157,7 +157,7 @@ gemm_kernel(int M, int N, int K, T alpha, const T* __restrict__ A, i64 lda,
 // float64 on the tensor cores: the same contract as gemm_kernel<double, ...> (all four transpositions, triangular K
 // ranges and masks, lower / mirror stores) with the inner product issued as mma.sync.m8n8k4.f64 -- the LAD / BP Gram
 // matrices and triangular solves (src/ADMMLAD.h:186-201, src/ADMMBP.h:167-182) are float64 in the reference and the
-// parity bar there is 1e-9, so no split-precision scheme applies.  128 x 128 x 16 tiles, 8 warps of 64 x 32, operands
+// parity bar there is 1e-9, so no split-precision scheme applies.  128 x 128 x 16 tiles, 16 warps of 32 x 32, operands
 // staged K-major in shared memory (row stride 132 doubles: the 4 x 4 lane pattern of a fragment load touches 16
 // distinct 8-byte banks), global loads prefetched into registers one K-slab ahead.  DFMA in IEEE order inside the
 // instruction: results differ from the CUDA-core kernel by summation order only.
@@ -169,12 +169,13 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
 }
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, i64 lda,
                     const double* __restrict__ B, i64 ldb, double beta, double* __restrict__ C, i64 ldc, int mode)
 {
     constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
-    constexpr int LA = BM * BK / 256, LB = BN * BK / 256;
+    constexpr int NT = 512;                                   // 16 warps of 32 x 32: four warps per scheduler
+    constexpr int LA = BM * BK / NT, LB = BN * BK / NT;
 
     const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
     if ((mode & GEMM_LOWER) && j0 > i0 + BM - 1) return;
@@ -191,12 +192,12 @@ gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict_
     __shared__ __align__(16) double Bs[BK][BN + PAD];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
     const int fr = lane >> 2, fk = lane & 3;                 // fragment row / column index, k index
 
-    double acc[8][4][2];
+    double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
@@ -204,7 +205,7 @@ gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict_
     auto fetch = [&](int k0) {
 #pragma unroll
         for (int l = 0; l < LA; l++) {
-            const int idx = tid + l * 256;
+            const int idx = tid + l * NT;
             int i, k;
             if (!TA) { i = idx % BM; k = idx / BM; } else { k = idx % BK; i = idx / BK; }
             const int gi = i0 + i, gk = k0 + k;
@@ -215,7 +216,7 @@ gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict_
         }
 #pragma unroll
         for (int l = 0; l < LB; l++) {
-            const int idx = tid + l * 256;
+            const int idx = tid + l * NT;
             int j, k;
             if (TB) { j = idx % BN; k = idx / BN; } else { k = idx % BK; j = idx / BK; }
             const int gj = j0 + j, gk = k0 + k;
@@ -228,14 +229,14 @@ gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict_
     auto stage = [&]() {
 #pragma unroll
         for (int l = 0; l < LA; l++) {
-            const int idx = tid + l * 256;
+            const int idx = tid + l * NT;
             int i, k;
             if (!TA) { i = idx % BM; k = idx / BM; } else { k = idx % BK; i = idx / BK; }
             As[k][i] = ra[l];
         }
 #pragma unroll
         for (int l = 0; l < LB; l++) {
-            const int idx = tid + l * 256;
+            const int idx = tid + l * NT;
             int j, k;
             if (TB) { j = idx % BN; k = idx / BN; } else { k = idx % BK; j = idx / BK; }
             Bs[k][j] = rb[l];
@@ -250,13 +251,13 @@ gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict_
         if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int k4 = 0; k4 < BK; k4 += 4) {
-            double a[8], b[4];
+            double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) a[mi] = As[k4 + fk][wm + mi * 8 + fr];
+            for (int mi = 0; mi < 4; mi++) a[mi] = As[k4 + fk][wm + mi * 8 + fr];
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) b[ni] = Bs[k4 + fk][wn + ni * 8 + fr];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++)
+            for (int mi = 0; mi < 4; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) dmma_8x8x4(acc[mi][ni], a[mi], b[ni]);
         }
@@ -264,7 +265,7 @@ gemm_f64_mma_kernel(int M, int N, int K, double alpha, const double* __restrict_
 
     const bool lower = (mode & GEMM_LOWER) != 0, mirror = (mode & GEMM_MIRROR) != 0;
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++) {
+    for (int mi = 0; mi < 4; mi++) {
         const int gi = i0 + wm + mi * 8 + fr;
         if (gi >= M) continue;
 #pragma unroll
@@ -288,10 +289,10 @@ static void gemm_f64_mma_launch(cudaStream_t s, bool ta, bool tb, i64 M, i64 N, 
                                 const double* B, i64 ldb, double beta, double* C, i64 ldc, int mode)
 {
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + 127) / 128));
-    if (!ta && !tb) gemm_f64_mma_kernel<false, false><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    else if (!ta && tb) gemm_f64_mma_kernel<false, true><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    else if (ta && !tb) gemm_f64_mma_kernel<true, false><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
-    else gemm_f64_mma_kernel<true, true><<<grid, 256, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    if (!ta && !tb) gemm_f64_mma_kernel<false, false><<<grid, 512, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else if (!ta && tb) gemm_f64_mma_kernel<false, true><<<grid, 512, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else if (ta && !tb) gemm_f64_mma_kernel<true, false><<<grid, 512, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
+    else gemm_f64_mma_kernel<true, true><<<grid, 512, 0, s>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, mode);
     KERNEL_CHECK();
 }
 
