@@ -117,6 +117,24 @@ def benchmark_data(n, p, m=100):
     return x, y, b
 
 
+def bp_benchmark_data(n, p, nsig):
+    """README.md:365-373 / :395-403: beta_true <- sample(c(runif(nsig), 0 ...)); x <- matrix(rnorm(n * p), n, p); y <- x %*% beta_true."""
+    r = RRng(123)
+    bt = np.concatenate([r.runif_vec(nsig), np.zeros(p - nsig)])
+    bt = r.sample_old(bt)
+    x = r.rnorm_vec(n * p).reshape(p, n).T.copy(order="F")
+    return x, x @ bt, bt
+
+
+def lad_benchmark_data(n, p):
+    """README.md:299-305: b <- runif(p); x <- matrix(rnorm(n * p, sd = 2), n, p); y <- x %*% b + rnorm(n)."""
+    r = RRng(123)
+    b = r.runif_vec(p)
+    x = r.rnorm_vec(n * p, 0.0, 2.0).reshape(p, n).T.copy(order="F")
+    y = x @ b + r.rnorm_vec(n)
+    return x, y, b
+
+
 def main():
     r = RRng(123)
     assert np.allclose(r.runif_vec(3), [0.2875775201246142, 0.7883051354438066, 0.4089769218116999], atol=1e-15)

@@ -224,3 +224,30 @@ def test_consensus_batched_passes_are_bit_identical(A, monkeypatch, n, p, N, max
     assert out["1"][2].shape == out["0"][2].shape and np.array_equal(out["1"][2], out["0"][2])
     if maxit == 45:
         assert (out["1"][1] == 46).any()
+
+
+def test_readme_benchmark_bp_and_lad_against_the_printed_ranges(A):
+    """The README's benchmark sections print range(beta_true - admm_bp$beta) (README.md:386-393) and range(rq.fit - admm_lad$beta)
+    (README.md:325-333) on data drawn with set.seed(123): the CUDA library against those digits directly (the oracle
+    reproduces every one of them, tests/test_oracle_readme_benchmarks.py).  BP's iterate path has restart-rule knife
+    edges (see test_bp_n500_p5000), LAD's converged point moves with the stopping iteration: solution-level bounds."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_readme_data import bp_benchmark_data, lad_benchmark_data
+    from scipy.optimize import linprog
+    import scipy.sparse as sp
+    x, y, bt = bp_benchmark_data(1000, 2000, 100)
+    f = A.admm_bp(x, y).fit()
+    d = bt - dense(f.beta)[:, 0]
+    print("\n[readme] GPU BP n=1000 p=2000: [%.9f, %.9f]  README [-0.001267782, 0.002108828]  niter %d (reference run: 78)" % (d.min(), d.max(), f.niter))
+    assert abs(d.min() - (-0.001267782)) < 3e-4 and abs(d.max() - 0.002108828) < 3e-4
+    n, p = 1000, 500
+    x, y, _ = lad_benchmark_data(n, p)
+    g = A.admm_lad(x, y, intercept=False).fit()
+    c = np.concatenate([np.zeros(p), np.ones(2 * n)])
+    Aeq = sp.hstack([sp.csr_matrix(x), sp.eye(n), -sp.eye(n)]).tocsr()
+    res = linprog(c, A_eq=Aeq, b_eq=y, bounds=[(None, None)] * p + [(0, None)] * (2 * n), method="highs")
+    dl = res.x[:p] - g.beta[1:]
+    print("[readme] GPU LAD n=1000 p=500: [%.9f, %.9f]  README [-0.006989109, 0.006061505]  niter %d (oracle: 211)" % (dl.min(), dl.max(), g.niter))
+    assert abs(dl.min() - (-0.006989109)) < 1e-3 and abs(dl.max() - 0.006061505) < 1e-3

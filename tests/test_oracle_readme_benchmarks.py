@@ -25,7 +25,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_readme_data import benchmark_data    # noqa: E402
+from make_readme_data import benchmark_data, bp_benchmark_data, lad_benchmark_data    # noqa: E402
 from oracle import pyoracle as O               # noqa: E402
 
 sk = pytest.importorskip("sklearn.linear_model")
@@ -107,3 +107,36 @@ def test_serial_wide_ranges_lie_inside_the_readme_band(wide, alpha, model, readm
     lo, hi, nl = diff_range(*wide, alpha, model, 1)
     print("\n[readme] p > n %s: oracle [%.9f, %.9f]  README [%.9f, %.9f] (%d lambdas)" % (model, lo, hi, readme[0], readme[1], nl))
     assert readme[0] < lo < 0.0 < hi < readme[1]
+
+
+# ---- basis pursuit and LAD: the README's benchmark sections print quantities the oracle can form on its own -----------
+# README.md:386-393 / :412-419: range(beta_true - admm_bp(x, y)$fit()$beta); README.md:325-333: range(rq.fit(x, y)$coefficients -
+# admm_lad(x, y, intercept = FALSE)$fit()$beta[-1]) with quantreg's exact simplex solution (here: the same LP through HiGHS).
+# The oracle reproduces every printed digit.
+
+@pytest.mark.parametrize("n,p,nsig,readme", [(1000, 2000, 100, (-0.001267782, 0.002108828)), (1000, 10000, 200, (-0.1575968, 0.3361001))])
+def test_bp_benchmark_ranges_are_reproduced_to_the_printed_digits(n, p, nsig, readme):
+    x, y, bt = bp_benchmark_data(n, p, nsig)
+    o = O.bp(x, y)
+    d = bt - o["beta"]
+    print("\n[readme] BP n=%d p=%d: oracle [%.9f, %.9f]  README [%.9f, %.9f]  niter %d" % (n, p, d.min(), d.max(), readme[0], readme[1], o["niter"]))
+    tol = 6e-10 if p == 2000 else 6e-8                      # half a unit of the last printed digit
+    assert abs(d.min() - readme[0]) < tol and abs(d.max() - readme[1]) < tol
+
+
+def test_lad_benchmark_range_is_reproduced_to_the_printed_digits():
+    from scipy.optimize import linprog
+    import scipy.sparse as sp
+    n, p = 1000, 500
+    x, y, _ = lad_benchmark_data(n, p)
+    o = O.lad(x, y, intercept=False)
+    # rq.fit(x, y): min sum(u + v) s.t. x b + u - v = y, u, v >= 0
+    c = np.concatenate([np.zeros(p), np.ones(2 * n)])
+    A = sp.hstack([sp.csr_matrix(x), sp.eye(n), -sp.eye(n)]).tocsr()
+    res = linprog(c, A_eq=A, b_eq=y, bounds=[(None, None)] * p + [(0, None)] * (2 * n), method="highs")
+    assert res.status == 0
+    d = res.x[:p] - o["beta"][1:]
+    print("\n[readme] LAD n=%d p=%d: LP - oracle [%.9f, %.9f]  README [-0.006989109, 0.006061505]  niter %d" % (n, p, d.min(), d.max(), o["niter"]))
+    assert abs(d.min() - (-0.006989109)) < 6e-10 and abs(d.max() - 0.006061505) < 6e-10
+    # (n = 5000, p = 1000, README [-0.003577610, 0.004135838] against quantreg's interior-point method: the oracle gives
+    #  [-0.003581140, 0.004106759] against the exact LP, which takes HiGHS eight minutes -- not run here)
