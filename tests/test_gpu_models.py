@@ -251,3 +251,24 @@ def test_readme_benchmark_bp_and_lad_against_the_printed_ranges(A):
     dl = res.x[:p] - g.beta[1:]
     print("[readme] GPU LAD n=1000 p=500: [%.9f, %.9f]  README [-0.006989109, 0.006061505]  niter %d (oracle: 211)" % (dl.min(), dl.max(), g.niter))
     assert abs(dl.min() - (-0.006989109)) < 1e-3 and abs(dl.max() - 0.006061505) < 1e-3
+
+
+def test_readme_benchmark_parallel_lasso_against_the_printed_minima(A):
+    """README.md:225-241 / :277-289: range(coef(glmnet) - admm_lasso(...)$parallel()$fit()$beta) over glmnet's lambda path.  The
+    minimum of those rows is the consensus solver's own error (glmnet is exact there): the CUDA library's two-block
+    consensus -- Woodbury blocks for p > n -- against the printed values, glmnet replaced by coordinate descent at 1e-10
+    (tests/test_oracle_readme_benchmarks.py holds the construction and the oracle's 7 / 4 digits)."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_readme_data import benchmark_data
+    from test_oracle_readme_benchmarks import glmnet_path
+    for (n, p, readme_min, tol) in ((1000, 2000, -0.001898237, 5e-5), (10000, 1000, -0.0005554722, 5e-5)):
+        x, y, _ = benchmark_data(n, p)
+        lam, bcd = glmnet_path(x, y, 1.0)
+        f = A.admm_lasso(x, y).penalty(list(lam)).parallel(2).fit()
+        d = bcd - dense(f.beta)
+        print("\n[readme] GPU padmm n=%d p=%d: [%.9f, %.9f]  README minimum %.9f  (%d lambdas, %d iterations)"
+              % (n, p, d.min(), d.max(), readme_min, len(lam), int(f.niter.sum())))
+        assert abs(d.min() - readme_min) < tol
