@@ -111,3 +111,32 @@ def test_align_traces_modulo_stutter_rows():
     wrong[4, 1] *= 1.001
     c = bench.align_traces(wrong, base, 1e-9)
     assert not c["ok"] and c["prefix"] == 4
+
+
+def test_recorded_bench_lines_carry_the_contract_keys():
+    """The committed bench lines of the round (profiles/): every key the measurement contract names, parity green."""
+    import glob
+    import json
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config", "roofline", "clocks", "gpu_launches"}
+    lines = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2D_bench_line.json")) + glob.glob(os.path.join(ROOT, "profiles", "r2v_bench_line_*gpu.json"))
+                   + glob.glob(os.path.join(ROOT, "profiles", "r2u_config_*.json")) + glob.glob(os.path.join(ROOT, "profiles", "r2B_config_wide.json"))
+                   + glob.glob(os.path.join(ROOT, "profiles", "r2z_config5_*.json")))
+    assert len(lines) >= 8
+    for path in lines:
+        d = json.loads(open(path).read().strip().splitlines()[-1])
+        assert need <= set(d), (path, need - set(d))
+        assert "workload" in d["config"] and "model" not in d["config"]
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
+        assert d["gpu_launches"] > 0
+        par = d.get("parity_vs_n1") or d.get("parity")
+        assert par and par["ok"] is True, path
+        if d["n_gpus"] == 1 and "consensus" not in d["config"]["workload"]:
+            assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r2u_bench_reference.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
+    assert ref["config"]["workload"] == json.loads(open(os.path.join(ROOT, "profiles", "r2u_bench.json")).read().strip().splitlines()[-1])["config"]["workload"]
