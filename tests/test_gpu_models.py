@@ -272,3 +272,29 @@ def test_readme_benchmark_parallel_lasso_against_the_printed_minima(A):
         print("\n[readme] GPU padmm n=%d p=%d: [%.9f, %.9f]  README minimum %.9f  (%d lambdas, %d iterations)"
               % (n, p, d.min(), d.max(), readme_min, len(lam), int(f.niter.sum())))
         assert abs(d.min() - readme_min) < tol
+
+
+def test_readme_benchmark_serial_lasso_and_enet_ranges(A):
+    """The serial rows of the README's timing sections (README.md:239-241, :287-289): range(coef(glmnet) - admm$beta) with glmnet
+    replaced by coordinate descent at 1e-10.  n > p: same sign, magnitude and shape as the printed ranges (they cannot agree
+    digit for digit: both extremes sit where the iterate's distance from the optimum depends on the stopping iteration);
+    p > n: inside the printed band, which is dominated by glmnet's own convergence threshold."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_readme_data import benchmark_data
+    from test_oracle_readme_benchmarks import glmnet_path
+    for (n, p, alpha, readme) in ((10000, 1000, 1.0, (-0.0002873333, 7.259293e-05)), (10000, 1000, 0.6, (-0.0002195360, 8.176991e-05)),
+                                  (1000, 2000, 1.0, (-0.001518947, 0.002055109)), (1000, 2000, 0.6, (-0.001615556, 0.001948477))):
+        x, y, _ = benchmark_data(n, p)
+        lam, bcd = glmnet_path(x, y, alpha)
+        m = A.admm_lasso(x, y).penalty(list(lam)) if alpha == 1.0 else A.admm_enet(x, y).penalty(list(lam), alpha=alpha)
+        f = m.fit()
+        d = bcd - dense(f.beta)
+        print("\n[readme] GPU %s n=%d p=%d: [%.9f, %.9f]  README [%.9f, %.9f]  (%d lambdas, %d iterations)"
+              % ("lasso" if alpha == 1.0 else "enet", n, p, d.min(), d.max(), readme[0], readme[1], len(lam), int(f.niter.sum())))
+        if n > p:
+            assert readme[0] * 2.5 < d.min() < readme[0] / 2.5 and readme[1] / 2.5 < d.max() < readme[1] * 2.5
+        else:
+            assert readme[0] < d.min() < 0.0 < d.max() < readme[1]
