@@ -15,8 +15,17 @@ ranges are formed with the oracle's solutions.  What the comparison can and cann
     because both extremes sit at lambdas where the iterate's distance from the optimum depends on the iteration the
     stopping rule fires at;
   * the serial p > n rows of the README ([-1.52e-3, 2.06e-3]) are dominated by glmnet's own convergence threshold (its
-    maximum 2.05e-3 is common to the admm and the padmm row): the oracle's deviation from the exact solution, 2e-4, lies
-    inside that band -- an upper bound only, so the wide solver stays unpinned by reference outputs.
+    maximum 2.05e-3 is common to the admm and the padmm row), so exact coordinate descent only bounds them from above.
+    With glmnet ITSELF restated at its default threshold (tests/glmnet_naive.py: glmnet 2.0's naive cycling with strong
+    rules, thresh = 1e-7) the printed numbers become comparable digit for digit, and the oracle's WIDE solver
+    (ADMMLassoWide / ADMMEnetWide, n < p) reproduces them at the end of the 100-lambda warm-started path:
+        lasso  README [-0.001518947, 0.002055109]   oracle [-0.001520026, 0.002054990]   (1.1e-6, 1.2e-7 = one float32 ulp of
+        enet   README [-0.001615556, 0.001948477]   oracle [-0.001618494, 0.001948417]    the coefficient 0.9329 behind it)
+    Both maxima sit on coefficient 11 (0.93) at the last two lambdas, where the ADMM iterate is 6e-6 / 1e-6 from the optimum:
+    what the README pins there is the wide solver's float32 iterate to one ulp.  The minima sit on a coefficient that
+    has just entered (0.0104); its value moves by 1e-6 per iteration around the stopping iteration.
+  * with the same restatement the $parallel() rows agree at BOTH ends: p > n [-0.001898237, 0.002052009] against
+    [-0.001898237, 0.002059639]; n > p [-0.0005554722, 7.382258e-05] against [-0.0005551146, 7.412061e-05].
 """
 import os
 import sys
@@ -27,6 +36,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
 from make_readme_data import benchmark_data, bp_benchmark_data, lad_benchmark_data    # noqa: E402
 from oracle import pyoracle as O               # noqa: E402
+from glmnet_naive import glmnet_gaussian_naive  # noqa: E402
 
 sk = pytest.importorskip("sklearn.linear_model")
 
@@ -72,8 +82,12 @@ def wide():
     return x, y
 
 
-def diff_range(x, y, alpha, model, nthread):
-    lam, bcd = glmnet_path(x, y, alpha)
+def diff_range(x, y, alpha, model, nthread, glmnet_itself=False):
+    """range(coef(glmnet) - admm$beta) with glmnet run to 1e-10 (scikit-learn) or restated at its default threshold."""
+    if glmnet_itself:
+        lam, bcd = glmnet_gaussian_naive(x, y, alpha)[:2]
+    else:
+        lam, bcd = glmnet_path(x, y, alpha)
     o = O.lasso_path(x, y, list(lam), model=model, alpha=alpha, nthread=nthread)
     d = bcd - o["beta"]
     return float(d.min()), float(d.max()), len(lam)
@@ -107,6 +121,41 @@ def test_serial_wide_ranges_lie_inside_the_readme_band(wide, alpha, model, readm
     lo, hi, nl = diff_range(*wide, alpha, model, 1)
     print("\n[readme] p > n %s: oracle [%.9f, %.9f]  README [%.9f, %.9f] (%d lambdas)" % (model, lo, hi, readme[0], readme[1], nl))
     assert readme[0] < lo < 0.0 < hi < readme[1]
+
+
+# ---- glmnet restated at its default threshold: the printed numbers digit for digit --------------------------------------
+
+def test_glmnet_restatement_agrees_with_exact_coordinate_descent(wide):
+    """The restatement against scikit-learn at 1e-10: same lambda grid, same path length, coefficients within the 2e-3 that
+    glmnet's thresh = 1e-7 leaves on this design -- and within 5e-6 (scikit-learn's own duality-gap tolerance) once its threshold is tightened to 1e-14."""
+    x, y = wide
+    lam, bcd = glmnet_path(x, y, 1.0)
+    lg, bg, rsq, nlp = glmnet_gaussian_naive(x, y, 1.0)
+    assert len(lg) == len(lam) == 100 and np.allclose(lg, lam, rtol=1e-12)
+    assert 1e-3 < np.abs(bg - bcd).max() < 2.2e-3
+    _, bt, _, _ = glmnet_gaussian_naive(x, y, 1.0, thresh=1e-14)
+    assert np.abs(bt - bcd).max() < 5e-6
+    assert np.all(np.diff(rsq) >= 0.0) and rsq[-1] < 0.999
+
+
+@pytest.mark.parametrize("alpha,model,readme,tol", [(1.0, "lasso", (-0.001518947, 0.002055109), (2e-6, 2.5e-7)),
+                                                    (0.6, "enet", (-0.001615556, 0.001948477), (4e-6, 1.5e-7))])
+def test_serial_wide_rows_are_reproduced_with_glmnet_at_its_default_threshold(wide, alpha, model, readme, tol):
+    """The reference-produced pin of the wide solver (ADMMLassoWide.h / ADMMEnetWide.h): see the module docstring."""
+    lo, hi, nl = diff_range(*wide, alpha, model, 1, glmnet_itself=True)
+    print("\n[readme] p > n %s vs glmnet(thresh = 1e-7): oracle [%.9f, %.9f]  README [%.9f, %.9f]  (off by %.1e, %.1e)"
+          % (model, lo, hi, readme[0], readme[1], abs(lo - readme[0]), abs(hi - readme[1])))
+    assert nl == 100
+    assert abs(lo - readme[0]) < tol[0] and abs(hi - readme[1]) < tol[1]
+
+
+def test_parallel_rows_are_reproduced_at_both_ends_with_glmnet_at_its_default_threshold(wide, tall):
+    lo, hi, _ = diff_range(*wide, 1.0, "lasso", 2, glmnet_itself=True)
+    print("\n[readme] p > n padmm vs glmnet(thresh = 1e-7): oracle [%.10f, %.9f]  README [-0.001898237, 0.002052009]" % (lo, hi))
+    assert abs(lo - (-0.001898237)) < 1e-9 and abs(hi - 0.002052009) < 1e-5
+    lo, hi, _ = diff_range(*tall, 1.0, "lasso", 2, glmnet_itself=True)
+    print("\n[readme] n > p padmm vs glmnet(thresh = 1e-7): oracle [%.10f, %.9f]  README [-0.0005554722, 7.382258e-05]" % (lo, hi))
+    assert abs(lo - (-0.0005554722)) < 5e-7 and abs(hi - 7.382258e-05) < 5e-7
 
 
 # ---- basis pursuit and LAD: the README's benchmark sections print quantities the oracle can form on its own -----------
