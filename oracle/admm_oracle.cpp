@@ -17,8 +17,12 @@
 //   /root/reference/src/DataStd.h:39-207          standardisation / recovery
 //   /root/reference/src/Lasso.cpp:39-135, Enet.cpp, ParLasso.cpp, LAD.cpp, BP.cpp   entry points
 // Parity pinning: tests/test_oracle_golden.py checks this file against the five result
-// vectors printed in /root/reference/README.md (the only reference-produced outputs that
-// exist); fixtures and the generating script live in tests/golden/.
+// vectors printed in /root/reference/README.md; tests/test_oracle_readme_benchmarks.py
+// against the coefficient-difference ranges the README prints for its timing sections
+// (BP / LAD: every printed digit; parallel lasso: 7 digits; the wide lasso / enet rows
+// of README.md:287-289 to 1e-6 / one float32 ulp, with glmnet restated at its default
+// threshold in tests/glmnet_naive.py).  These are the only reference-produced outputs
+// that exist; fixtures and the generating scripts live in tests/golden/.
 //
 // Mixed precision follows the reference: scalars (rho, eps, residuals, acceleration
 // coefficients) are double; lasso/enet/consensus vectors are float; LAD/BP are double.

@@ -298,3 +298,25 @@ def test_readme_benchmark_serial_lasso_and_enet_ranges(A):
             assert readme[0] * 2.5 < d.min() < readme[0] / 2.5 and readme[1] / 2.5 < d.max() < readme[1] * 2.5
         else:
             assert readme[0] < d.min() < 0.0 < d.max() < readme[1]
+
+
+def test_readme_benchmark_wide_rows_against_glmnet_at_its_default_threshold(A):
+    """README.md:287-289, p > n: range(coef(glmnet(x, y)) - admm$beta) with glmnet ITSELF restated at thresh = 1e-7
+    (tests/glmnet_naive.py), so that the printed numbers are comparable digit for digit: the library's wide solver at the end
+    of the 100-lambda warm-started path against numbers the reference's ADMMLassoWide / ADMMEnetWide produced."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_readme_data import benchmark_data
+    from glmnet_naive import glmnet_gaussian_naive
+    x, y, _ = benchmark_data(1000, 2000)
+    for (alpha, readme, tol) in ((1.0, (-0.001518947, 0.002055109), (5e-6, 1e-6)), (0.6, (-0.001615556, 0.001948477), (8e-6, 1e-6))):
+        lam, bg = glmnet_gaussian_naive(x, y, alpha)[:2]
+        m = A.admm_lasso(x, y).penalty(list(lam)) if alpha == 1.0 else A.admm_enet(x, y).penalty(list(lam), alpha=alpha)
+        f = m.fit()
+        d = bg - dense(f.beta)
+        print("\n[readme] GPU %s n=1000 p=2000 vs glmnet(thresh = 1e-7): [%.9f, %.9f]  README [%.9f, %.9f]  (off by %.1e, %.1e; %d iterations)"
+              % ("lasso" if alpha == 1.0 else "enet", d.min(), d.max(), readme[0], readme[1], abs(d.min() - readme[0]),
+                 abs(d.max() - readme[1]), int(f.niter.sum())))
+        assert abs(d.min() - readme[0]) < tol[0] and abs(d.max() - readme[1]) < tol[1]
