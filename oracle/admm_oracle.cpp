@@ -39,6 +39,10 @@ using namespace oracle;
 
 namespace {
 
+// ncv of the Spectra call behind the default rho / gamma.  3 = the reference's source as it stands (ADMMLassoTall.h:196,
+// ADMMLassoWide.h:202); settable through oracle_set_lanczos_ncv for the README forensics of tests/test_oracle_golden.py only.
+int g_lanczos_ncv = 3;
+
 struct Trace {           // optional per-iteration record for parity tests
     double* buf = nullptr;   // rows of 5: eps_primal, resid_primal, eps_dual, resid_dual, rho
     int cap = 0;
@@ -237,7 +241,7 @@ struct TallLasso {
         if (s.rho <= 0) {
             const float* Gp = G.data(); const i64 pp = p;
             float ev = coarse_largest_eigenvalue<float>(
-                [Gp, pp](const float* v, float* w) { symv_lower(Gp, pp, v, w); }, p, &lz);
+                [Gp, pp](const float* v, float* w) { symv_lower(Gp, pp, v, w); }, p, &lz, 10, 0.1f, g_lanczos_ncv);
             if (lz.converged < 0) return -3;
             ev_estimate = ev;
             s.rho = std::pow((double)ev, 1.0 / 3) * std::pow((double)lambda, 2.0 / 3);
@@ -331,7 +335,7 @@ struct WideLasso {
         gram_nt_lower(X, n, p, G.data());
         const float* Gp = G.data(); const i64 nn = n;
         sprad = coarse_largest_eigenvalue<float>(
-            [Gp, nn](const float* v, float* w) { symv_lower(Gp, nn, v, w); }, n, &lz);
+            [Gp, nn](const float* v, float* w) { symv_lower(Gp, nn, v, w); }, n, &lz, 10, 0.1f, g_lanczos_ncv);
     }
     void set_enet(double alpha_) { enet = true; alpha = (float)alpha_; lambda0 = float(lambda0 / (alpha + 0.0001)); }
     void init(double lambda_, double rho_)
@@ -765,11 +769,14 @@ int oracle_standardize_f32(float* X, float* Y, i64 n, i64 p, int standardize, in
     return 0;
 }
 
+// see g_lanczos_ncv; returns the previous value
+int oracle_set_lanczos_ncv(int ncv) { const int old = g_lanczos_ncv; g_lanczos_ncv = ncv; return old; }
+
 // coarse lambda_max of the symmetric matrix whose lower triangle is in S (n x n)
 float oracle_coarse_eig_f32(const float* S, i64 n, int* info3)
 {
     LanczosInfo li;
-    float ev = coarse_largest_eigenvalue<float>([S, n](const float* v, float* w) { symv_lower(S, n, v, w); }, n, &li);
+    float ev = coarse_largest_eigenvalue<float>([S, n](const float* v, float* w) { symv_lower(S, n, v, w); }, n, &li, 10, 0.1f, g_lanczos_ncv);
     if (info3) { info3[0] = li.nmatvec; info3[1] = li.nrestart; info3[2] = li.converged; }
     return ev;
 }

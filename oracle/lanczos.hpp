@@ -132,19 +132,22 @@ struct LanczosInfo {
 // Throws nothing; returns NaN and sets info->converged = -1 for n < 3 (the reference's
 // constructor would throw std::invalid_argument there).
 template <class T, class Op>
-T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart = 10, T tol = T(0.1))
+T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart = 10, T tol = T(0.1), int ncv = 3)
 {
-    const int m = 3;                    // ncv
+    // ncv = 3 is what the reference's source has today; other values (2..8) exist for the README forensics in
+    // tests/test_oracle_golden.py only (the README was knitted by a build with ncv = 2, see there).
+    constexpr int MM = 8;
+    const int m = std::min(std::max(ncv, 2), MM);
     const int nev = 1;
     LanczosInfo li;
-    if (n < 3) { li.converged = -1; if (info) *info = li; return std::numeric_limits<T>::quiet_NaN(); }
+    if (n < m) { li.converged = -1; if (info) *info = li; return std::numeric_limits<T>::quiet_NaN(); }
     const T prec = std::pow(std::numeric_limits<T>::epsilon(), T(2) / T(3));
 
     std::vector<T> V((size_t)n * m, T(0)), f(n), w(n), tmp(n);
-    T H[m * m];                          // column-major; H(r,c) = H[c*m + r]
+    T H[MM * MM];                        // column-major; H(r,c) = H[c*m + r]
     for (int i = 0; i < m * m; i++) H[i] = T(0);
     auto Hat = [&](int r, int c) -> T& { return H[c * m + r]; };
-    T ritz_val[m] = {0, 0, 0}, ritz_est[m] = {0, 0, 0};
+    T ritz_val[MM] = {0}, ritz_est[MM] = {0};
 
     // --- start vector and first step (init) ---
     {
@@ -171,7 +174,7 @@ T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart =
                 // breakdown: draw a new direction orthogonal to the current basis
                 LehmerStream rng(2 * i);
                 rng.fill(f.data(), n);
-                T Vf[m];
+                T Vf[MM];
                 for (int c = 0; c < i; c++) Vf[c] = dot(V.data() + (size_t)c * n, f.data(), n);
                 for (int c = 0; c < i; c++) {
                     const T* vc = V.data() + (size_t)c * n;
@@ -195,7 +198,7 @@ T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart =
             }
             beta = norm2(f.data(), n);
             // re-orthogonalise against the first i+1 basis vectors, at most 5 passes
-            T Vf[m];
+            T Vf[MM];
             auto project = [&]() {
                 T mx = T(0);
                 for (int c = 0; c <= i; c++) {
@@ -223,12 +226,18 @@ T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart =
 
     // Ritz values of H sorted descending, with the last components of their vectors
     auto ritz = [&]() {
-        T d[m], e[m], Q[m * m];
+        T d[MM], e[MM], Q[MM * MM];
         for (int i = 0; i < m; i++) d[i] = Hat(i, i);
         for (int i = 0; i < m - 1; i++) e[i] = Hat(i + 1, i);
         tridiag_eig_small<T>(m, d, e, Q);
-        int idx[m] = {0, 1, 2};
-        std::sort(idx, idx + m, [&](int a, int b) { return -d[a] < -d[b]; });
+        int idx[MM];
+        for (int i = 0; i < m; i++) idx[i] = i;
+        for (int i = 1; i < m; i++) {                                   // descending (LARGEST_ALGE), insertion sort
+            const int t = idx[i];
+            int j = i;
+            while (j > 0 && -d[t] < -d[idx[j - 1]]) { idx[j] = idx[j - 1]; j--; }
+            idx[j] = t;
+        }
         for (int i = 0; i < m; i++) { ritz_val[i] = d[idx[i]]; ritz_est[i] = Q[idx[i] * m + (m - 1)]; }
     };
 
@@ -251,19 +260,19 @@ T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart =
         li.nrestart++;
 
         // shifted QR sweeps with the unwanted Ritz values
-        T Q[m * m];
+        T Q[MM * MM];
         for (int i = 0; i < m * m; i++) Q[i] = T(0);
         for (int i = 0; i < m; i++) Q[i * m + i] = T(1);
         for (int sidx = k; sidx < m; sidx++) {
             const T mu = ritz_val[sidx];
             for (int i = 0; i < m; i++) Hat(i, i) -= mu;
             // QR of the tridiagonal: Givens sequence (cs, sn), R kept in Tm
-            T Tm[m * m];
+            T Tm[MM * MM];
             for (int i = 0; i < m * m; i++) Tm[i] = T(0);
             auto Tat = [&](int r, int c) -> T& { return Tm[c * m + r]; };
             for (int i = 0; i < m; i++) Tat(i, i) = Hat(i, i);
             for (int i = 0; i < m - 1; i++) { Tat(i, i + 1) = Hat(i + 1, i); Tat(i + 1, i) = Hat(i + 1, i); }
-            T cs[m - 1], sn[m - 1];
+            T cs[MM], sn[MM];
             const T eps = std::numeric_limits<T>::epsilon();
             for (int i = 0; i < m - 1; i++) {
                 T a = Tat(i, i), b = Tat(i + 1, i);
@@ -287,7 +296,7 @@ T coarse_largest_eigenvalue(Op&& op, i64 n, LanczosInfo* info, int max_restart =
                     Q[(i + 1) * m + r] = sn[i] * t + cs[i] * Q[(i + 1) * m + r];
                 }
             // H <- R Q (tridiagonal again), then undo the shift
-            T RQ[m * m];
+            T RQ[MM * MM];
             for (int i = 0; i < m * m; i++) RQ[i] = T(0);
             auto Rat = [&](int r, int c) -> T& { return RQ[c * m + r]; };
             for (int i = 0; i < m; i++) Rat(i, i) = Tat(i, i);

@@ -108,6 +108,23 @@ def lasso_path(x, y, lambdas=None, nlambda=100, lambda_min_ratio=None, standardi
                 rho=aux[0], eig=aux[1], lambda0=aux[2], scaleY=aux[3], meanY=aux[4])
 
 
+class lanczos_ncv:
+    """with lanczos_ncv(2): ...  -- the Spectra call behind the default rho / gamma run with another ncv (README forensics only;
+    3 is the reference's source as it stands)."""
+
+    def __init__(self, ncv):
+        self.ncv = int(ncv)
+
+    def __enter__(self):
+        lib().oracle_set_lanczos_ncv.restype = C.c_int
+        self.old = lib().oracle_set_lanczos_ncv(C.c_int(self.ncv))
+        return self
+
+    def __exit__(self, *exc):
+        lib().oracle_set_lanczos_ncv(C.c_int(self.old))
+        return False
+
+
 def lad(x, y, intercept=True, maxit=10000, eps_abs=1e-4, eps_rel=1e-4, rho=1.0, trace_cap=0):
     x = np.asfortranarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)

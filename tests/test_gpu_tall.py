@@ -69,6 +69,27 @@ def test_readme_lasso(A, O, lasso_xy):
     assert abs(f.info["rho"] - o["rho"]) < 1e-5 * o["rho"]
 
 
+def test_readme_tall_columns_at_print_precision_with_the_rho_of_the_build_that_knitted_them(A, O, lasso_xy):
+    """The README was knitted by a build whose Spectra call kept two Lanczos vectors (tests/test_oracle_golden.py); the library
+    follows today's source (ncv = 3), so the rho of that build is handed over through opts(rho = ...): both tall columns
+    of the README then come out of the CUDA library within 3e-6 / 4e-6 (the intercept, 5.36, carries 6 float32 ulps of
+    the recover step's summation order; coefficients within 1.3e-6) against 1.2e-5 for the lasso column with the default rho."""
+    x, y = lasso_xy
+    with O.lanczos_ncv(2):
+        rho_l = O.lasso_path(x, y, [LAM])["rho"]
+        rho_e = O.lasso_path(x, y, [LAM], model="enet", alpha=0.5)["rho"]
+    f = A.admm_lasso(x, y).penalty(LAM).opts(rho=rho_l).fit()
+    bl = dense(f.beta)[:, 0]
+    g = A.admm_enet(x, y).penalty(LAM, alpha=0.5).opts(rho=rho_e).fit()
+    be = dense(g.beta)[:, 0]
+    print("\n[readme] GPU with the README build's rho: lasso column %.2e (niter %d), enet column %.2e (niter %d)"
+          % (np.abs(bl - R.LASSO_ADMM).max(), int(f.niter[0]), np.abs(be - R.ENET_ADMM).max(), int(g.niter[0])))
+    assert np.abs(bl - R.LASSO_ADMM).max() < 5e-6 and np.array_equal(bl != 0, R.LASSO_ADMM != 0) and int(f.niter[0]) == 31
+    assert np.abs(be - R.ENET_ADMM).max() < 5e-6 and np.array_equal(be != 0, R.ENET_ADMM != 0) and int(g.niter[0]) == 22
+    f0 = A.admm_lasso(x, y).penalty(LAM).fit()
+    assert np.abs(dense(f0.beta)[:, 0] - R.LASSO_ADMM).max() > 8e-6                 # today's source (ncv = 3)
+
+
 def test_readme_enet(A, O, lasso_xy):
     x, y = lasso_xy
     f = A.admm_enet(x, y).penalty(LAM, alpha=0.5).fit()

@@ -10,10 +10,16 @@ ranges are formed with the oracle's solutions.  What the comparison can and cann
     oracle reproduces it to 7 digits for p > n (README -0.001898237; two Woodbury blocks of 500 rows) and to 4 digits
     for n > p (README -0.0005554722) -- a reference-produced number for PADMMLasso_Master / _Worker incl. the Woodbury
     branch, for the glmnet lambda grid and for the data generator;
-  * the serial n > p rows agree in sign, order of magnitude and shape (README [-2.87e-4, 7.26e-5] lasso,
-    [-2.20e-4, 8.18e-5] enet; oracle [-3.14e-4, 8.88e-5], [-3.42e-4, 4.94e-5]); they cannot agree digit for digit
-    because both extremes sit at lambdas where the iterate's distance from the optimum depends on the iteration the
-    stopping rule fires at;
+  * the serial n > p rows (README [-2.87e-4, 7.26e-5] lasso, [-2.20e-4, 8.18e-5] enet; oracle with today's source
+    [-3.14e-4, 9.9e-5], [-3.42e-4, 7.5e-5]): their MINIMA sit on the second / third lambda of the path (20 iterations from
+    a cold start, iterate 3e-4 from the optimum) and depend smoothly on rho; a rho scan puts them -- independently for lasso
+    and elastic net -- at 0.9950 +- 0.0003 of the default rho, i.e. at a Lanczos estimate 1.5 % below the one the source as
+    it stands produces.  That is exactly the estimate of the same Spectra call with ncv = 2 instead of 3 (15 866 against
+    16 121), which also reproduces BOTH README example columns at print precision (tests/test_oracle_golden.py): with it
+    the minima come out at -0.0002875345 (README -0.0002873333) and -0.0002196403 (README -0.0002195360), 2e-7 and 1e-7
+    away.  The MAXIMA cannot agree digit for digit under any rho: they are either glmnet's own error (7.2-7.4e-5 on two
+    coefficients at lambda 53-54) or, when one of the last lambdas stops after 4-8 iterations, 9e-5 -- which of the two
+    happens flips with rho at the 5e-4 level;
   * the serial p > n rows of the README ([-1.52e-3, 2.06e-3]) are dominated by glmnet's own convergence threshold (its
     maximum 2.05e-3 is common to the admm and the padmm row), so exact coordinate descent only bounds them from above.
     With glmnet ITSELF restated at its default threshold (tests/glmnet_naive.py: glmnet 2.0's naive cycling with strong
@@ -156,6 +162,21 @@ def test_parallel_rows_are_reproduced_at_both_ends_with_glmnet_at_its_default_th
     lo, hi, _ = diff_range(*tall, 1.0, "lasso", 2, glmnet_itself=True)
     print("\n[readme] n > p padmm vs glmnet(thresh = 1e-7): oracle [%.10f, %.9f]  README [-0.0005554722, 7.382258e-05]" % (lo, hi))
     assert abs(lo - (-0.0005554722)) < 5e-7 and abs(hi - 7.382258e-05) < 5e-7
+
+
+@pytest.mark.parametrize("alpha,model,readme_min,off3", [(1.0, "lasso", -0.0002873333, 2.7e-5), (0.6, "enet", -0.0002195360, 1.2e-4)])
+def test_serial_tall_minima_are_reproduced_with_two_lanczos_vectors(tall, alpha, model, readme_min, off3):
+    """The README was knitted by a build whose Spectra call had ncv = 2 (module docstring, tests/test_oracle_golden.py)."""
+    lam, bg = glmnet_gaussian_naive(*tall, alpha)[:2]
+    o3 = O.lasso_path(*tall, list(lam), model=model, alpha=alpha)
+    with O.lanczos_ncv(2):
+        o2 = O.lasso_path(*tall, list(lam), model=model, alpha=alpha)
+    lo3, lo2 = float((bg - o3["beta"]).min()), float((bg - o2["beta"]).min())
+    print("\n[readme] n > p %s minimum: ncv = 3 (eig %.1f) %.10f, ncv = 2 (eig %.1f) %.10f, README %.10f"
+          % (model, o3["eig"], lo3, o2["eig"], lo2, readme_min))
+    assert abs(o3["eig"] - 16120.7) < 0.5 and abs(o2["eig"] - 15866.2) < 0.5
+    assert abs(lo2 - readme_min) < 4e-7                       # 2.0e-7 / 1.0e-7 in practice
+    assert 0.5 * off3 < abs(lo3 - readme_min) < 2 * off3      # today's source: 2.7e-5 / 1.2e-4 away
 
 
 # ---- basis pursuit and LAD: the README's benchmark sections print quantities the oracle can form on its own -----------
