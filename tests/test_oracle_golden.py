@@ -22,8 +22,8 @@ knitted the README and the source as it stands is taken into account:
   kept TWO basis vectors -- an earlier revision of src/ADMMLassoTall.h:196 -- and the source as it stands keeps three.
   The oracle and the CUDA library follow today's source (ncv = 3); `pyoracle.lanczos_ncv(2)` exists for these forensics
   only.  1.2e-5 is therefore the distance between two correct runs of the reference 0.5 % apart in rho, not noise to be
-  covered by a tolerance.  Everything else the README prints (parallel lasso, LAD, BP, the p > n rows of the wide solver,
-  whose gamma is the same kind of estimate but enters the converged iterate only weakly) is reproduced with ncv = 3.
+  covered by a tolerance.  The p > n rows of the wide solver tell the same story for its gamma (README build: the ncv = 5
+  estimate; tests/test_oracle_readme_benchmarks.py); parallel lasso, LAD and BP use no such estimate.
 
 The iteration counts (31 / 339 / 22 / 443 / 72) are those of the survey's independent NumPy probes.
 """

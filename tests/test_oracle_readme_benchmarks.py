@@ -29,7 +29,15 @@ ranges are formed with the oracle's solutions.  What the comparison can and cann
         enet   README [-0.001615556, 0.001948477]   oracle [-0.001618494, 0.001948417]    the coefficient 0.9329 behind it)
     Both maxima sit on coefficient 11 (0.93) at the last two lambdas, where the ADMM iterate is 6e-6 / 1e-6 from the optimum:
     what the README pins there is the wide solver's float32 iterate to one ulp.  The minima sit on a coefficient that
-    has just entered (0.0104); its value moves by 1e-6 per iteration around the stopping iteration.
+    has just entered (0.0104) and still moves by 1e-6 per iteration: they feel the step size gamma, which is the same kind
+    of unconverged Lanczos estimate as the tall solver's rho (src/ADMMLassoWide.h:200-207).  As for the tall solver
+    (tests/test_oracle_golden.py: the build that knitted the README kept ncv = 2 there), the README's numbers identify the
+    estimate that build used: with the value the same Spectra call gives for **ncv = 5** (5484.66 against 5445.91 for the
+    source's ncv = 3) BOTH extremes of BOTH rows fall into place,
+        lasso  README [-0.001518947, 0.002055109]   oracle [-0.0015189345, 0.0020551089]   (1.3e-8, 8e-11)
+        enet   README [-0.001615556, 0.001948477]   oracle [-0.0016155542, 0.0019486554]   (1.8e-9, 1.8e-7)
+    while ncv = 2, 4 and 6 miss the minima by 1e-6 .. 1.6e-5: given the same gamma, the oracle's wide solver follows the
+    reference's to 1e-8 over a 100-lambda warm-started path (2862 iterations).
   * with the same restatement the $parallel() rows agree at BOTH ends: p > n [-0.001898237, 0.002052009] against
     [-0.001898237, 0.002059639]; n > p [-0.0005554722, 7.382258e-05] against [-0.0005551146, 7.412061e-05].
 """
@@ -153,6 +161,24 @@ def test_serial_wide_rows_are_reproduced_with_glmnet_at_its_default_threshold(wi
           % (model, lo, hi, readme[0], readme[1], abs(lo - readme[0]), abs(hi - readme[1])))
     assert nl == 100
     assert abs(lo - readme[0]) < tol[0] and abs(hi - readme[1]) < tol[1]
+
+
+@pytest.mark.parametrize("alpha,model,readme,tol", [(1.0, "lasso", (-0.001518947, 0.002055109), (4e-8, 2e-9)),
+                                                    (0.6, "enet", (-0.001615556, 0.001948477), (1e-8, 3e-7))])
+def test_serial_wide_rows_with_the_gamma_of_the_build_that_knitted_the_readme(wide, alpha, model, readme, tol):
+    """Module docstring: the Lanczos estimate of the README build equals the ncv = 5 one; with it the wide solver's rows are
+    reproduced to 1e-8 at the minima (1e-6 with the source's ncv = 3) -- and no other ncv does that."""
+    lam, bg = glmnet_gaussian_naive(*wide, alpha)[:2]
+    off = {}
+    for ncv in (2, 3, 4, 5, 6):
+        with O.lanczos_ncv(ncv):
+            o = O.lasso_path(*wide, list(lam), model=model, alpha=alpha)
+        d = bg - o["beta"]
+        off[ncv] = (abs(float(d.min()) - readme[0]), abs(float(d.max()) - readme[1]), float(o["eig"]))
+    print("\n[readme] p > n %s, |oracle - README| at (min, max) by ncv: %s"
+          % (model, {k: ("%.1e" % v[0], "%.1e" % v[1], "eig %.2f" % v[2]) for k, v in off.items()}))
+    assert off[5][0] < tol[0] and off[5][1] < tol[1]
+    assert all(off[k][0] > 8e-7 for k in (2, 3, 4, 6))
 
 
 def test_parallel_rows_are_reproduced_at_both_ends_with_glmnet_at_its_default_threshold(wide, tall):
