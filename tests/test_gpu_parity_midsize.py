@@ -2,7 +2,8 @@
 C ABI.  Each test prints its MEASURED deviation (`-s` / the GPU test log shows them) next to the bound it asserts.
 
 Stated tolerances (float32 paths, same X, y, lambda; rho from each side's own Lanczos run):
-    coefficients  max|dbeta| <= 1e-4 * max(1, |beta|_inf)  on the original scale, per lambda,
+    coefficients  max|dbeta| <= 1e-4 * max(1, |beta|_inf)  on the original scale, per lambda (1.5e-4 for the 30-lambda p = 2048 path,
+                  where two oracle runs with different BLAS thread counts are themselves 1.2e-4 apart),
     support       identical outside a band of 1e-4 * max(1, |beta|_inf) (coordinates that one side holds at exactly 0
                   and the other at less than the band; their number is printed),
     iterations    total within 3 % (the stopping rule compares float32 norms accumulated in different orders).
@@ -19,7 +20,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def O():
     from oracle import pyoracle
-    pyoracle.use_openblas(0)
+    pyoracle.use_openblas(16)       # a FIXED thread count: the float32 SYRK's summation order, and with it single stopping iterations, depend on it
     return pyoracle
 
 
@@ -72,7 +73,9 @@ def test_tall_p2048_pipelined_host_ingest(A, O, monkeypatch):
     o = O.lasso_path(x, y, nlambda=30)
     assert np.allclose(f.lambda_, o["lambda_"], rtol=1e-5)
     assert abs(f.info["rho"] / o["rho"] - 1) < 1e-4
-    report("tall p=2048 n=40000 30 lambda", dense(f.beta), o["beta"], f.niter, o["niter"], 1e-4, 1e-4)
+    # 1.5e-4 here: two runs of the ORACLE that differ only in the BLAS thread count of its float32 Gram matrix (16 against 4)
+    # are already 1.2e-4 apart on this problem (33 stopping iterations moved); measured GPU-vs-oracle 5.5e-4 = 0.84e-4 * |beta|_inf
+    report("tall p=2048 n=40000 30 lambda", dense(f.beta), o["beta"], f.niter, o["niter"], 1.5e-4, 1e-4)
 
 
 def test_tall_ill_conditioned_explicit_inverse(A, O):
